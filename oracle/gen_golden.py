@@ -1,0 +1,237 @@
+"""Generate tests/golden/* by running the REFERENCE's own code (build container only).
+
+    python oracle/gen_golden.py [--only snippets,coalign,xattn,ddim,pipeline]
+
+/root/reference is imported read-only with the recipe of SURVEY.md App. C (the
+`rollingdepth` package __init__ is bypassed, PyAV is stubbed, one transformers
+constant is shimmed).  The fixtures are small and are committed together with
+this script; nothing at test / bench time reads /root/reference.
+"""
+from __future__ import annotations
+
+import argparse
+import contextlib
+import importlib.util
+import io
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+REF = "/root/reference"
+
+
+def import_reference():
+    import transformers.utils as tu
+    tu.FLAX_WEIGHTS_NAME = "flax_model.msgpack"                       # shim 1
+    sys.modules.setdefault("av", types.ModuleType("av"))              # shim 2
+    sys.path.insert(0, f"{REF}/diffusers/src")
+    sys.dont_write_bytecode = True
+    import diffusers  # noqa: F401
+    pkg = types.ModuleType("rollingdepth")
+    pkg.__path__ = [f"{REF}/rollingdepth"]
+    sys.modules["rollingdepth"] = pkg                                 # detour around __init__
+
+    def load(n):
+        s = importlib.util.spec_from_file_location(f"rollingdepth.{n}", f"{REF}/rollingdepth/{n}.py")
+        m = importlib.util.module_from_spec(s)
+        sys.modules[f"rollingdepth.{n}"] = m
+        s.loader.exec_module(m)
+        return m
+
+    load("video_io")
+    da = load("depth_aligner")
+    rp = load("rollingdepth_pipeline")
+    return da, rp
+
+
+# --------------------------------------------------------------------------- snippets
+def gen_snippets(da, rp):
+    P = rp.RollingDepthPipeline
+    cases = []
+    for seq_len in (7, 16, 30, 150):
+        for n in (2, 3, 4):
+            for d in (1, 4, 10, 25):
+                dc = P.cap_max_dilation(seq_len=seq_len, snippet_len=n, dilation=d, verbose=False)
+                if dc < 1:
+                    continue
+                idx = P.get_snippet_indice(0, torch.zeros(1), seq_len, n, dc, dc, 1)
+                cases.append(dict(kind="init", seq_len=seq_len, snippet_len=n, dilation=d, capped=dc, idx=idx))
+    for seq_len, start, total in ((16, 5, 10), (150, 6, 10), (40, 6, 5), (150, 6, 20), (30, 4, 7)):
+        for i_step in range(total):
+            idx = P.get_snippet_indice(i_step, torch.zeros(total), seq_len, 3, start, 1, 1)
+            cases.append(dict(kind="refine", seq_len=seq_len, snippet_len=3, start=start, total=total,
+                              i_step=i_step, idx=idx))
+    with open(os.path.join(GOLD, "snippets.json"), "w") as f:
+        json.dump(cases, f)
+    print("snippets:", len(cases), "cases")
+
+
+# --------------------------------------------------------------------------- co-alignment
+def synth_snippets(N, H, W, w, dilations, seed, dtype=torch.float32, noise=0.01):
+    """Aligner microbench generator of SURVEY.md section 8d (smooth base, per-snippet affine)."""
+    g = torch.Generator().manual_seed(seed)
+    base = torch.rand(N, 1, H // 4 + 2, W // 4 + 2, generator=g)
+    base = torch.nn.functional.interpolate(base, size=(H, W), mode="bilinear", align_corners=False)
+    base = 0.2 + 0.6 * (base - base.min()) / (base.max() - base.min())
+    out = []
+    for d in dilations:
+        n = N - (w - 1) * d
+        idx = torch.arange(n)[:, None] + torch.arange(w)[None, :] * d
+        s = 1.0 + 0.3 * torch.rand(n, 1, 1, 1, 1, generator=g)
+        t = 0.1 * torch.rand(n, 1, 1, 1, 1, generator=g)
+        x = (base[idx] - t) / s + noise * torch.randn(n, w, 1, H, W, generator=g)
+        out.append(x.to(dtype))
+    return out
+
+
+def gen_coalign(da, rp):
+    from torch.optim.adam import Adam
+
+    snaps = []
+
+    class RecordingAdam(Adam):
+        def step(self, closure=None):
+            # state BEFORE the update + gradient at that state + params AFTER
+            params = [p for g in self.param_groups for p in g["params"]]
+            pre = [p.detach().clone() for p in params]
+            st = [(self.state[p]["exp_avg"].clone(), self.state[p]["exp_avg_sq"].clone(),
+                   int(self.state[p]["step"])) if len(self.state[p]) else None for p in params]
+            loss = super().step(closure)
+            snaps.append(dict(pre=pre, state=st, grad=[p.grad.detach().clone() for p in params],
+                              post=[p.detach().clone() for p in params], loss=float(loss)))
+            return loss
+
+    da.Adam = RecordingAdam
+    out = {}
+    for tag, (N, H, W, w, dil, dtype, iters) in {
+        "a": (14, 34, 44, 3, [1, 4], torch.float32, 40),
+        "b": (20, 44, 54, 3, [1, 3, 6], torch.float32, 25),
+        "h": (14, 34, 44, 3, [1, 4], torch.float16, 12),
+        "w2": (9, 24, 34, 2, [1, 2], torch.float32, 10),
+    }.items():
+        snaps.clear()
+        sn = synth_snippets(N, H, W, w, dil, seed=7, dtype=dtype)
+        al = da.DepthAligner(device=torch.device("cpu"), num_iterations=iters)
+        with contextlib.redirect_stdout(io.StringIO()):
+            merged, scales, trans, hist = al.run(snippet_ls=[s.clone() for s in sn], dilations=list(dil))
+        G = len(dil)
+        out[f"{tag}_meta"] = np.array([N, H, W, w, iters, G] + list(dil), dtype=np.int64)
+        for i, s in enumerate(sn):
+            out[f"{tag}_snip{i}"] = s.numpy()
+        out[f"{tag}_merged"] = merged.detach().numpy()
+        for i in range(G):
+            out[f"{tag}_scale{i}"] = scales[i].detach().reshape(-1).numpy()
+            out[f"{tag}_trans{i}"] = trans[i].detach().reshape(-1).numpy()
+        out[f"{tag}_hist"] = np.array(hist, dtype=np.float64)
+        # teacher-forcing snapshots at a few iterations: params are [s_0..s_G-1, t_0..t_G-1]
+        for it in sorted({0, 1, 5, iters - 1}):
+            sp = snaps[it]
+            for i in range(2 * G):
+                out[f"{tag}_it{it}_pre{i}"] = sp["pre"][i].reshape(-1).numpy()
+                out[f"{tag}_it{it}_grad{i}"] = sp["grad"][i].reshape(-1).numpy()
+                out[f"{tag}_it{it}_post{i}"] = sp["post"][i].reshape(-1).numpy()
+                if sp["state"][i] is not None:
+                    out[f"{tag}_it{it}_m{i}"] = sp["state"][i][0].reshape(-1).numpy()
+                    out[f"{tag}_it{it}_v{i}"] = sp["state"][i][1].reshape(-1).numpy()
+            out[f"{tag}_it{it}_step"] = np.array(it, dtype=np.int64)
+        print(f"coalign {tag}: loss {hist[0][0]:.6f} -> {hist[-1][0]:.6f}")
+    np.savez_compressed(os.path.join(GOLD, "coalign.npz"), **out)
+
+
+# --------------------------------------------------------------------------- attention processor
+def gen_xattn(da, rp):
+    from diffusers.models.attention_processor import Attention, AttnProcessor2_0
+
+    out = {}
+    torch.manual_seed(3)
+    for tag, (C, heads, n, hw, cross) in {
+        "self": (128, 2, 3, 40, None),
+        "self_odd": (192, 3, 4, 21, None),
+        "text": (128, 2, 3, 40, 96),
+        "perframe": (128, 2, 3, 40, None),
+    }.items():
+        attn = Attention(query_dim=C, cross_attention_dim=cross, heads=heads, dim_head=64, bias=False)
+        attn.set_processor(AttnProcessor2_0())
+        x = torch.randn(n, hw, C)
+        ctx = None if cross is None else torch.randn(1, 2, cross)
+        nv = None if tag == "perframe" else n
+        with torch.no_grad():
+            y = attn(x, encoder_hidden_states=ctx, num_view=nv)
+        out[f"{tag}_x"] = x.numpy()
+        out[f"{tag}_y"] = y.numpy()
+        out[f"{tag}_meta"] = np.array([C, heads, n, hw, cross or 0, -1 if nv is None else nv], dtype=np.int64)
+        if ctx is not None:
+            out[f"{tag}_ctx"] = ctx.numpy()
+        out[f"{tag}_wq"] = attn.to_q.weight.detach().numpy()
+        out[f"{tag}_wk"] = attn.to_k.weight.detach().numpy()
+        out[f"{tag}_wv"] = attn.to_v.weight.detach().numpy()
+        out[f"{tag}_wo"] = attn.to_out[0].weight.detach().numpy()
+        out[f"{tag}_bo"] = attn.to_out[0].bias.detach().numpy()
+    np.savez_compressed(os.path.join(GOLD, "xattn.npz"), **out)
+    print("xattn:", [k for k in out if k.endswith("_y")])
+
+
+# --------------------------------------------------------------------------- DDIM
+def gen_ddim(da, rp):
+    from diffusers import DDIMScheduler
+
+    out = {}
+    g = torch.Generator().manual_seed(11)
+    for tag, kw in {
+        "vtrail": dict(prediction_type="v_prediction", timestep_spacing="trailing"),
+        "epslead": dict(prediction_type="epsilon", timestep_spacing="leading", steps_offset=1),
+    }.items():
+        sch = DDIMScheduler(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012,
+                            beta_schedule="scaled_linear", clip_sample=False, set_alpha_to_one=False, **kw)
+        out[f"{tag}_alphas"] = sch.alphas_cumprod.numpy()
+        for n in (1, 10, 20):
+            sch.set_timesteps(n)
+            ts = sch.timesteps.clone()
+            out[f"{tag}_ts{n}"] = ts.numpy()
+            for dt, dn in ((torch.float32, "f32"), (torch.float16, "f16")):
+                x = torch.randn(3, 4, 6, 5, generator=g).to(dt)
+                v = torch.randn(3, 4, 6, 5, generator=g).to(dt)
+                for pos in sorted({0, len(ts) - 1}):
+                    y = sch.step(v, ts[pos], x).prev_sample
+                    out[f"{tag}_n{n}_{dn}_p{pos}_x"] = x.numpy()
+                    out[f"{tag}_n{n}_{dn}_p{pos}_v"] = v.numpy()
+                    out[f"{tag}_n{n}_{dn}_p{pos}_y"] = y.numpy()
+                if n == 20:
+                    z = sch.add_noise(x, v, ts[10])
+                    out[f"{tag}_addnoise_{dn}_x"] = x.numpy()
+                    out[f"{tag}_addnoise_{dn}_n"] = v.numpy()
+                    out[f"{tag}_addnoise_{dn}_y"] = z.numpy()
+                    out[f"{tag}_addnoise_t"] = np.array(int(ts[10]))
+    np.savez_compressed(os.path.join(GOLD, "ddim.npz"), **out)
+    print("ddim ok")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="snippets,coalign,xattn,ddim,pipeline")
+    args = ap.parse_args()
+    os.makedirs(GOLD, exist_ok=True)
+    da, rp = import_reference()
+    todo = args.only.split(",")
+    if "snippets" in todo:
+        gen_snippets(da, rp)
+    if "coalign" in todo:
+        gen_coalign(da, rp)
+    if "xattn" in todo:
+        gen_xattn(da, rp)
+    if "ddim" in todo:
+        gen_ddim(da, rp)
+    if "pipeline" in todo:
+        from oracle import gen_golden_pipeline
+        gen_golden_pipeline.run(da, rp, GOLD)
+
+
+if __name__ == "__main__":
+    sys.path.insert(0, ROOT)
+    main()
