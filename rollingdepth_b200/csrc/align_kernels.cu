@@ -1,0 +1,978 @@
+// Depth co-alignment kernels (sm_100a): global min, crop/subsample, the fused per-iteration
+// optimisation pass (closed-form gradient + Adam), overlap-average merge, renormalisation.
+//
+// Replaces rollingdepth/depth_aligner.py:68-262 and rollingdepth_pipeline.py:316-318 of the
+// reference.  All of these are HBM-bound streaming kernels: coalesced vector loads, warp-shuffle
+// reductions, no atomics on floats (results are deterministic run to run).
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace rd {
+
+// =============================================================================================
+// Generic "block partials -> last block reduces" helper used by min / minmax reductions
+// =============================================================================================
+constexpr int kRedMaxBlocks = 16384;
+struct RedScratch {
+    float part_min[kRedMaxBlocks];
+    float part_max[kRedMaxBlocks];
+    unsigned int counter;
+};
+
+struct SegList {
+    const void* ptr[RD_MAX_GROUPS];
+    long long count[RD_MAX_GROUPS];
+    int nseg;
+};
+
+template <typename T> struct Vec16 { static constexpr int N = 16 / sizeof(T); };
+
+template <typename T>
+__device__ __forceinline__ void unpack16(const uint4& u, float* out) {
+    if constexpr (sizeof(T) == 4) {
+        out[0] = __uint_as_float(u.x); out[1] = __uint_as_float(u.y);
+        out[2] = __uint_as_float(u.z); out[3] = __uint_as_float(u.w);
+    } else {
+        const T* h = reinterpret_cast<const T*>(&u);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[i] = Cvt<T>::to_f(h[i]);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) global_min_kernel(SegList segs, RedScratch* sc, float* out_min) {
+    float mn = INFINITY;
+    constexpr int VN = Vec16<T>::N;
+    for (int sgi = 0; sgi < segs.nseg; ++sgi) {
+        const T* base = reinterpret_cast<const T*>(segs.ptr[sgi]);
+        const long long n = segs.count[sgi];
+        // head elements until 16-byte alignment
+        long long head = ((16 - (reinterpret_cast<uintptr_t>(base) & 15)) & 15) / sizeof(T);
+        if (head > n) head = n;
+        const long long nvec = (n - head) / VN;
+        const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        const long long gstride = (long long)gridDim.x * blockDim.x;
+        if (gtid < head) mn = fminf(mn, Cvt<T>::to_f(base[gtid]));
+        const uint4* vp = reinterpret_cast<const uint4*>(base + head);
+        long long i = gtid;
+        // 4 independent 16-byte loads in flight per thread
+        for (; i + 3 * gstride < nvec; i += 4 * gstride) {
+            uint4 a = ldg_stream16(vp + i), b = ldg_stream16(vp + i + gstride);
+            uint4 c = ldg_stream16(vp + i + 2 * gstride), d = ldg_stream16(vp + i + 3 * gstride);
+            float f[VN];
+            unpack16<T>(a, f);
+#pragma unroll
+            for (int q = 0; q < VN; ++q) mn = fminf(mn, f[q]);
+            unpack16<T>(b, f);
+#pragma unroll
+            for (int q = 0; q < VN; ++q) mn = fminf(mn, f[q]);
+            unpack16<T>(c, f);
+#pragma unroll
+            for (int q = 0; q < VN; ++q) mn = fminf(mn, f[q]);
+            unpack16<T>(d, f);
+#pragma unroll
+            for (int q = 0; q < VN; ++q) mn = fminf(mn, f[q]);
+        }
+        for (; i < nvec; i += gstride) {
+            float f[VN];
+            unpack16<T>(ldg_stream16(vp + i), f);
+#pragma unroll
+            for (int q = 0; q < VN; ++q) mn = fminf(mn, f[q]);
+        }
+        const long long tail0 = head + nvec * VN;
+        if (tail0 + gtid < n) mn = fminf(mn, Cvt<T>::to_f(base[tail0 + gtid]));
+    }
+    __shared__ float sh[8];
+    __shared__ bool last;
+    mn = warp_min(mn);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = mn;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = sh[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fminf(m, sh[w]);
+        sc->part_min[blockIdx.x] = m;
+        __threadfence();
+        unsigned prev = atomicAdd(&sc->counter, 1u);
+        last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last) {
+        float m = INFINITY;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) m = fminf(m, __ldcg(&sc->part_min[i]));
+        m = warp_min(m);
+        if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = m;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float r = sh[0];
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = fminf(r, sh[w]);
+            out_min[0] = r;
+            sc->counter = 0;
+        }
+    }
+}
+
+// =============================================================================================
+// prep: (x - min) in the snippet dtype, border crop, stride-`factor` subsample
+// =============================================================================================
+struct PrepParams {
+    const void* snip[RD_MAX_GROUPS];
+    rd_coalign_problem pb;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) prep_kernel(PrepParams pp, const float* dev_min, T* out) {
+    const rd_coalign_problem& pb = pp.pb;
+    const long long total = (long long)pb.n_total * pb.w * pb.P_pad;
+    const float mn = dev_min[0];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(i % pb.P_pad);
+        const long long rj = i / pb.P_pad;  // row * w + j
+        float v = 0.f;
+        if (p < pb.P) {
+            const int row = (int)(rj / pb.w);
+            int g = 0;
+#pragma unroll
+            for (int q = 1; q < RD_MAX_GROUPS; ++q)
+                if (q < pb.G && row >= pb.row0[q]) g = q;
+            const long long local = rj - (long long)pb.row0[g] * pb.w;  // k * w + j inside group g
+            const int hs = p / pb.Ws, ws = p % pb.Ws;
+            const int h = pb.border + hs * pb.factor, w = pb.border + ws * pb.factor;
+            const T* src = reinterpret_cast<const T*>(pp.snip[g]);
+            const float x = Cvt<T>::to_f(src[(local * pb.H + h) * pb.W + w]);
+            v = Cvt<T>::round(__fsub_rn(x, mn));  // torch: arithmetic in fp32, rounded once to the tensor dtype
+        }
+        out[i] = Cvt<T>::from_f(v);
+    }
+}
+
+// =============================================================================================
+// The fused optimisation pass
+// =============================================================================================
+constexpr int kPassThreads = 128;
+constexpr int kPassV = 2;                 // pixels per thread per step
+constexpr int kPassItersPerChunk = 4;     // target steps per (frame, chunk) work item
+constexpr int kFrameStats = 8;            // sum|target|, sum|tdep|, L1, L2, tmin, tmax, pad, pad
+
+struct PassParams {
+    const void* x;
+    int G, w, N, P, P_pad, R, C, n_total, steps_per_frame;
+    int d[RD_MAX_GROUPS], n[RD_MAX_GROUPS], row0[RD_MAX_GROUPS];
+    int f_begin;
+    int apply_update;
+    float step_size, bc2_sqrt, beta1, beta2, eps;
+    float lmda2, lmda3, dlw, ls_over_Z, inv_P;
+    const float* theta_in;   // [6][n_total] : s, t, m_s, m_t, v_s, v_t
+    float* theta_out;
+    const float* gterm_in;   // [N][R][2] from the previous pass (after exchange)
+    float* gterm_out;        // [N][R][2] written by this pass
+    float* part;             // [N][C][4R + kFrameStats]
+    unsigned int* counter;   // [N]
+    float* hist_frame;       // [N][4] for this pass: loss term, soft term, tmin, tmax
+};
+
+__device__ __forceinline__ void adam_update(float& theta, float& m, float& v, float g, const PassParams& p) {
+    // torch.optim.Adam single-tensor path: lerp for m, mul/addcmul for v, addcdiv for theta
+    m = m + (g - m) * (1.f - p.beta1);
+    v = v * p.beta2 + (1.f - p.beta2) * g * g;
+    const float denom = __fdiv_rn(sqrtf(v), p.bc2_sqrt) + p.eps;
+    theta = theta - __fdiv_rn(p.step_size * m, denom);
+}
+
+template <typename T, int V>
+__device__ __forceinline__ void load_px(const T* ptr, float* out) {
+    static_assert(V == 2, "V == 2 only");
+    if constexpr (sizeof(T) == 4) {
+        const uint2 u = ldg_stream8(ptr);
+        out[0] = __uint_as_float(u.x);
+        out[1] = __uint_as_float(u.y);
+    } else {
+        const uint32_t u = ldg_stream4(ptr);
+        const T* h = reinterpret_cast<const T*>(&u);
+        out[0] = Cvt<T>::to_f(h[0]);
+        out[1] = Cvt<T>::to_f(h[1]);
+    }
+}
+
+template <int RM>
+struct PassAcc {
+    float A0[RM], A1[RM], D0[RM], D1[RM];
+    float fa, fb, l1, l2, tmin, tmax;
+};
+
+template <int RM, int V, bool MASK>
+__device__ __forceinline__ void pass_step(PassAcc<RM>& acc, const float (&xv)[RM][V], const int (&rows)[RM],
+                                          const float (&sc)[RM], const float (&tc)[RM], float cntf, int nvalid_px) {
+    float inv[RM][V];
+    float sy[V], si[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) { sy[v] = 0.f; si[v] = 0.f; }
+#pragma unroll
+    for (int c = 0; c < RM; ++c) {
+        if (rows[c] >= 0) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const float y = fmaf(sc[c], xv[c][v], tc[c]);
+                const float iv = __frcp_rn(fmaxf(y, 1e-3f));
+                inv[c][v] = iv;
+                sy[v] += y;
+                si[v] += iv;
+            }
+        }
+    }
+    float tg[V], td[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        tg[v] = __fdiv_rn(sy[v], cntf);
+        td[v] = __fdiv_rn(si[v], cntf);
+        const bool ok = !MASK || (v < nvalid_px);
+        if (ok) {
+            acc.fa += fabsf(tg[v]);
+            acc.fb += fabsf(td[v]);
+            acc.tmin = fminf(acc.tmin, tg[v]);
+            acc.tmax = fmaxf(acc.tmax, tg[v]);
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < RM; ++c) {
+        if (rows[c] >= 0) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const bool ok = !MASK || (v < nvalid_px);
+                if (ok) {
+                    const float x = xv[c][v];
+                    const float y = fmaf(sc[c], x, tc[c]);
+                    const float r1 = y - tg[v];
+                    const float sg = (r1 > 0.f ? 1.f : 0.f) - (r1 < 0.f ? 1.f : 0.f);
+                    acc.l1 += fabsf(r1);
+                    acc.A0[c] += sg;
+                    acc.A1[c] = fmaf(sg, x, acc.A1[c]);
+                    const float iv = inv[c][v];
+                    const float r2 = iv - td[v];
+                    const float sd = (r2 > 0.f ? 1.f : 0.f) - (r2 < 0.f ? 1.f : 0.f);
+                    acc.l2 += fabsf(r2);
+                    const float wg = (y >= 1e-3f) ? sd * iv * iv : 0.f;
+                    acc.D0[c] += wg;
+                    acc.D1[c] = fmaf(wg, x, acc.D1[c]);
+                }
+            }
+        }
+    }
+}
+
+template <typename T, int RM>
+__global__ void __launch_bounds__(kPassThreads) coalign_pass_kernel(const PassParams p) {
+    constexpr int V = kPassV;
+    constexpr int NV = 4 * RM + kFrameStats;
+    __shared__ int sh_row[RM];
+    __shared__ float sh_s[RM], sh_t[RM], sh_soft[RM];
+    __shared__ float sh_red[kPassThreads / 32][NV];
+    __shared__ float sh_tot[NV];
+    __shared__ int sh_last;
+
+    const int tid = threadIdx.x;
+    const int ch = blockIdx.x;
+    const int f = p.f_begin + blockIdx.y;
+    const int R = p.R, nt = p.n_total;
+
+    // ---------------- prologue: parameters of the <= R snippets touching this frame ----------
+    if (tid < RM) {
+        int row = -1;
+        float s = 0.f, t = 0.f, soft = 0.f;
+        if (tid < R) {
+            const int g = tid / p.w, j = tid - g * p.w;
+            const int d = p.d[g];
+            const int k = f - j * d;
+            if (k >= 0 && k < p.n[g]) {
+                row = p.row0[g] + k;
+                s = __ldcg(p.theta_in + row);
+                t = __ldcg(p.theta_in + nt + row);
+                const float ng = (float)p.n[g];
+                if (p.apply_update) {
+                    float ms = __ldcg(p.theta_in + 2 * nt + row), mt = __ldcg(p.theta_in + 3 * nt + row);
+                    float vs = __ldcg(p.theta_in + 4 * nt + row), vt = __ldcg(p.theta_in + 5 * nt + row);
+                    float gs = 0.f, gt = 0.f;
+                    for (int jj = 0; jj < p.w; ++jj) {
+                        const int fp = k + jj * d;
+                        const float2 gg = __ldcg(reinterpret_cast<const float2*>(p.gterm_in) + (size_t)fp * R + g * p.w + jj);
+                        gs += gg.x;
+                        gt += gg.y;
+                    }
+                    gs += -2.f * p.lmda2 * fmaxf(1.f - s, 0.f) / ng;
+                    gt += 2.f * p.lmda3 * t / ng;
+                    adam_update(s, ms, vs, gs, p);
+                    adam_update(t, mt, vt, gt, p);
+                    if (ch == 0) {
+                        // every frame touching this snippet writes the same bits (deterministic recompute)
+                        p.theta_out[row] = s;           p.theta_out[nt + row] = t;
+                        p.theta_out[2 * nt + row] = ms; p.theta_out[3 * nt + row] = mt;
+                        p.theta_out[4 * nt + row] = vs; p.theta_out[5 * nt + row] = vt;
+                    }
+                }
+                if (j == 0) {
+                    const float hinge = fmaxf(1.f - s, 0.f);
+                    soft = (p.lmda2 * hinge * hinge + p.lmda3 * t * t) / ng;
+                }
+            }
+        }
+        sh_row[tid] = row;
+        sh_s[tid] = s;
+        sh_t[tid] = t;
+        sh_soft[tid] = soft;
+    }
+    __syncthreads();
+    if (ch == 0 && tid == 0) {
+        float soft = 0.f;
+        for (int c = 0; c < R; ++c) soft += sh_soft[c];
+        p.hist_frame[(size_t)f * 4 + 1] = soft;
+    }
+
+    int rows[RM];
+    float sc[RM], tc[RM];
+    const T* xp[RM];
+    int cnt = 0;
+#pragma unroll
+    for (int c = 0; c < RM; ++c) {
+        rows[c] = sh_row[c];
+        sc[c] = sh_s[c];
+        tc[c] = sh_t[c];
+        const int j = c % p.w;
+        xp[c] = reinterpret_cast<const T*>(p.x) + ((size_t)(rows[c] < 0 ? 0 : rows[c]) * p.w + j) * p.P_pad;
+        cnt += rows[c] >= 0;
+    }
+    const float cntf = (float)cnt;
+
+    PassAcc<RM> acc;
+#pragma unroll
+    for (int c = 0; c < RM; ++c) { acc.A0[c] = acc.A1[c] = acc.D0[c] = acc.D1[c] = 0.f; }
+    acc.fa = acc.fb = acc.l1 = acc.l2 = 0.f;
+    acc.tmin = INFINITY;
+    acc.tmax = -INFINITY;
+
+    // ---------------- main loop over this chunk's pixel steps --------------------------------
+    const int base = p.steps_per_frame / p.C, rem = p.steps_per_frame % p.C;
+    const int st0 = ch * base + min(ch, rem);
+    const int st1 = st0 + base + (ch < rem ? 1 : 0);
+    for (int st = st0; st < st1; ++st) {
+        const int p0 = (st * kPassThreads + tid) * V;
+        if (p0 >= p.P) continue;
+        float xv[RM][V];
+#pragma unroll
+        for (int c = 0; c < RM; ++c) {
+            if (rows[c] >= 0) load_px<T, V>(xp[c] + p0, xv[c]);
+        }
+        if (p0 + V <= p.P) pass_step<RM, V, false>(acc, xv, rows, sc, tc, cntf, V);
+        else               pass_step<RM, V, true>(acc, xv, rows, sc, tc, cntf, p.P - p0);
+    }
+
+    // ---------------- block reduction -> part[f][ch][*] ---------------------------------------
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int c = 0; c < RM; ++c) {
+        const float a0 = warp_sum(acc.A0[c]), a1 = warp_sum(acc.A1[c]);
+        const float d0 = warp_sum(acc.D0[c]), d1 = warp_sum(acc.D1[c]);
+        if (lane == 0) {
+            sh_red[warp][4 * c + 0] = a0; sh_red[warp][4 * c + 1] = a1;
+            sh_red[warp][4 * c + 2] = d0; sh_red[warp][4 * c + 3] = d1;
+        }
+    }
+    {
+        const float fa = warp_sum(acc.fa), fb = warp_sum(acc.fb), l1 = warp_sum(acc.l1), l2 = warp_sum(acc.l2);
+        const float mn = warp_min(acc.tmin), mx = warp_max(acc.tmax);
+        if (lane == 0) {
+            float* r = &sh_red[warp][4 * RM];
+            r[0] = fa; r[1] = fb; r[2] = l1; r[3] = l2; r[4] = mn; r[5] = mx; r[6] = 0.f; r[7] = 0.f;
+        }
+    }
+    __syncthreads();
+    float* part_f = p.part + (size_t)f * p.C * NV;
+    if (tid < NV) {
+        float v = sh_red[0][tid];
+        const int q = tid - 4 * RM;
+#pragma unroll
+        for (int w = 1; w < kPassThreads / 32; ++w) {
+            const float o = sh_red[w][tid];
+            v = (q == 4) ? fminf(v, o) : (q == 5) ? fmaxf(v, o) : v + o;
+        }
+        if (p.C == 1) sh_tot[tid] = v;
+        else part_f[(size_t)ch * NV + tid] = v;
+    }
+    if (p.C > 1) {
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned prev = atomicAdd(&p.counter[f], 1u);
+            sh_last = (prev == (unsigned)(p.C - 1));
+        }
+        __syncthreads();
+        if (!sh_last) return;
+        __threadfence();
+        if (tid < NV) {
+            float v = __ldcg(part_f + tid);
+            const int q = tid - 4 * RM;
+            for (int c2 = 1; c2 < p.C; ++c2) {
+                const float o = __ldcg(part_f + (size_t)c2 * NV + tid);
+                v = (q == 4) ? fminf(v, o) : (q == 5) ? fmaxf(v, o) : v + o;
+            }
+            sh_tot[tid] = v;
+        }
+        if (tid == 0) p.counter[f] = 0;
+    }
+    __syncthreads();
+
+    // ---------------- last chunk of the frame: per-frame scales, gradient terms, loss term ----
+    const float a = sh_tot[4 * RM + 0] * p.inv_P;   // mean_p |target|   (depth_aligner.py:197)
+    const float b = sh_tot[4 * RM + 1] * p.inv_P;   // mean_p |target_depth|
+    const float ia = __fdiv_rn(1.f, a), ib = __fdiv_rn(1.f, b);
+    if (tid < R) {
+        float2 gg = make_float2(0.f, 0.f);
+        if (sh_row[tid] >= 0) {
+            const float A0 = sh_tot[4 * tid + 0], A1 = sh_tot[4 * tid + 1];
+            const float D0 = sh_tot[4 * tid + 2], D1 = sh_tot[4 * tid + 3];
+            gg.x = p.ls_over_Z * (A1 * ia - p.dlw * D1 * ib);   // d loss / d s  (data term)
+            gg.y = p.ls_over_Z * (A0 * ia - p.dlw * D0 * ib);   // d loss / d t
+        }
+        reinterpret_cast<float2*>(p.gterm_out)[(size_t)f * R + tid] = gg;
+    }
+    if (tid == 0) {
+        float* h = p.hist_frame + (size_t)f * 4;
+        h[0] = p.ls_over_Z * (sh_tot[4 * RM + 2] * ia + p.dlw * sh_tot[4 * RM + 3] * ib);
+        h[2] = sh_tot[4 * RM + 4];
+        h[3] = sh_tot[4 * RM + 5];
+    }
+}
+
+// final Adam update for snippets whose first frame lies in [f_begin, f_end)
+__global__ void coalign_final_update_kernel(PassParams p, int f_begin, int f_end, float* s, float* t, float* m_s,
+                                            float* m_t, float* v_s, float* v_t) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= p.n_total) return;
+    int g = 0;
+    for (int q = 1; q < p.G; ++q)
+        if (row >= p.row0[q]) g = q;
+    const int k = row - p.row0[g];
+    const int nt = p.n_total;
+    float so = 0.f, to = 0.f, ms = 0.f, mt = 0.f, vs = 0.f, vt = 0.f;
+    if (k >= f_begin && k < f_end) {
+        so = p.theta_in[row]; to = p.theta_in[nt + row];
+        ms = p.theta_in[2 * nt + row]; mt = p.theta_in[3 * nt + row];
+        vs = p.theta_in[4 * nt + row]; vt = p.theta_in[5 * nt + row];
+        if (p.apply_update) {
+            float gs = 0.f, gt = 0.f;
+            for (int jj = 0; jj < p.w; ++jj) {
+                const int fp = k + jj * p.d[g];
+                const float2 gg = reinterpret_cast<const float2*>(p.gterm_in)[(size_t)fp * p.R + g * p.w + jj];
+                gs += gg.x;
+                gt += gg.y;
+            }
+            const float ng = (float)p.n[g];
+            gs += -2.f * p.lmda2 * fmaxf(1.f - so, 0.f) / ng;
+            gt += 2.f * p.lmda3 * to / ng;
+            adam_update(so, ms, vs, gs, p);
+            adam_update(to, mt, vt, gt, p);
+        }
+    }
+    s[row] = so; t[row] = to; m_s[row] = ms; m_t[row] = mt; v_s[row] = vs; v_t[row] = vt;
+}
+
+// history[it] = (sum_f loss_f + soft_f, min_f, max_f) over owned frames; one block per iteration
+__global__ void __launch_bounds__(256) coalign_history_kernel(const float* hist_frame, int N, int f_begin, int f_end,
+                                                              float* history) {
+    const int it = blockIdx.x;
+    const float* h = hist_frame + (size_t)it * N * 4;
+    float sum = 0.f, mn = INFINITY, mx = -INFINITY;
+    for (int f = f_begin + threadIdx.x; f < f_end; f += blockDim.x) {
+        sum += h[(size_t)f * 4 + 0] + h[(size_t)f * 4 + 1];
+        mn = fminf(mn, h[(size_t)f * 4 + 2]);
+        mx = fmaxf(mx, h[(size_t)f * 4 + 3]);
+    }
+    __shared__ float sh[3][8];
+    sum = warp_sum(sum); mn = warp_min(mn); mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = sum; sh[1][threadIdx.x >> 5] = mn; sh[2][threadIdx.x >> 5] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { sum += sh[0][w]; mn = fminf(mn, sh[1][w]); mx = fmaxf(mx, sh[2][w]); }
+        history[3 * it + 0] = sum; history[3 * it + 1] = mn; history[3 * it + 2] = mx;
+    }
+}
+
+// =============================================================================================
+// merge: per-frame mean of ((x - min) * s + t) in the snippet dtype + min/max of the result
+// =============================================================================================
+struct MergeParams {
+    const void* snip[RD_MAX_GROUPS];
+    rd_coalign_problem pb;
+    const float* s;
+    const float* t;
+    const float* dev_min;
+    void* out;
+    RedScratch* sc;
+    float* out_minmax;
+    int blocks_per_frame;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) merge_kernel(MergeParams mp) {
+    const rd_coalign_problem& pb = mp.pb;
+    constexpr int VN = Vec16<T>::N;
+    __shared__ const T* sh_ptr[RD_MAX_GROUPS * RD_MAX_WINDOW];
+    __shared__ float sh_s[RD_MAX_GROUPS * RD_MAX_WINDOW], sh_t[RD_MAX_GROUPS * RD_MAX_WINDOW];
+    __shared__ int sh_cnt;
+    const int f = blockIdx.y;
+    const long long HW = (long long)pb.H * pb.W;
+    if (threadIdx.x == 0) {
+        int cnt = 0;
+        // reference order: for each dilation, boolean mask over [n, w] row-major => k ascending (j descending)
+        for (int g = 0; g < pb.G; ++g) {
+            for (int j = pb.w - 1; j >= 0; --j) {
+                const int k = f - j * pb.d[g];
+                if (k >= 0 && k < pb.n[g]) {
+                    const int row = pb.row0[g] + k;
+                    sh_ptr[cnt] = reinterpret_cast<const T*>(mp.snip[g]) + ((long long)k * pb.w + j) * HW;
+                    sh_s[cnt] = Cvt<T>::round(mp.s[row]);   // s.to(dtype)  (depth_aligner.py:248)
+                    sh_t[cnt] = Cvt<T>::round(mp.t[row]);   // t.to(dtype)
+                    ++cnt;
+                }
+            }
+        }
+        sh_cnt = cnt;
+    }
+    __syncthreads();
+    const int cnt = sh_cnt;
+    const float cntf = (float)cnt;
+    const float mn0 = mp.dev_min[0];
+    T* out = reinterpret_cast<T*>(mp.out) + (long long)f * HW;
+    float lmin = INFINITY, lmax = -INFINITY;
+    // all per-frame planes are 16-byte aligned when HW % VN == 0 and the bases are aligned (checked on host)
+    const long long nvec = HW / VN;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+         i += (long long)gridDim.x * blockDim.x) {
+        float acc[VN];
+#pragma unroll
+        for (int q = 0; q < VN; ++q) acc[q] = 0.f;
+        for (int c = 0; c < cnt; ++c) {
+            float xv[VN];
+            unpack16<T>(ldg_stream16(reinterpret_cast<const uint4*>(sh_ptr[c]) + i), xv);
+            const float sT = sh_s[c], tT = sh_t[c];
+#pragma unroll
+            for (int q = 0; q < VN; ++q) {
+                const float a = Cvt<T>::round(__fsub_rn(xv[q], mn0));   // snippet - mn      (:79)
+                const float b = Cvt<T>::round(__fmul_rn(a, sT));        // * s.to(dtype)     (:248)
+                acc[q] += Cvt<T>::round(__fadd_rn(b, tT));              // + t.to(dtype)     (:249)
+            }
+        }
+        alignas(16) T res[VN];
+#pragma unroll
+        for (int q = 0; q < VN; ++q) {
+            const float m = Cvt<T>::round(__fdiv_rn(acc[q], cntf));  // torch mean: fp32 sum / count, rounded once
+            res[q] = Cvt<T>::from_f(m);
+            lmin = fminf(lmin, m);
+            lmax = fmaxf(lmax, m);
+        }
+        *reinterpret_cast<uint4*>(out + i * VN) = *reinterpret_cast<const uint4*>(res);
+    }
+    // scalar tail (HW not a multiple of the vector width)
+    for (long long i = nvec * VN + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < HW;
+         i += (long long)gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int c = 0; c < cnt; ++c) {
+            const float a = Cvt<T>::round(__fsub_rn(Cvt<T>::to_f(sh_ptr[c][i]), mn0));
+            const float b = Cvt<T>::round(__fmul_rn(a, sh_s[c]));
+            acc += Cvt<T>::round(__fadd_rn(b, sh_t[c]));
+        }
+        const float m = Cvt<T>::round(__fdiv_rn(acc, cntf));
+        out[i] = Cvt<T>::from_f(m);
+        lmin = fminf(lmin, m);
+        lmax = fmaxf(lmax, m);
+    }
+    // min / max of the merged video (for rollingdepth_pipeline.py:316-317)
+    __shared__ float shm[2][8];
+    __shared__ bool last;
+    lmin = warp_min(lmin); lmax = warp_max(lmax);
+    if ((threadIdx.x & 31) == 0) { shm[0][threadIdx.x >> 5] = lmin; shm[1][threadIdx.x >> 5] = lmax; }
+    __syncthreads();
+    const unsigned nblk = gridDim.x * gridDim.y;
+    const unsigned bid = blockIdx.y * gridDim.x + blockIdx.x;
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { lmin = fminf(lmin, shm[0][w]); lmax = fmaxf(lmax, shm[1][w]); }
+        mp.sc->part_min[bid] = lmin;
+        mp.sc->part_max[bid] = lmax;
+        __threadfence();
+        last = (atomicAdd(&mp.sc->counter, 1u) == nblk - 1);
+    }
+    __syncthreads();
+    if (last) {
+        float a = INFINITY, b = -INFINITY;
+        for (unsigned i = threadIdx.x; i < nblk; i += blockDim.x) {
+            a = fminf(a, __ldcg(&mp.sc->part_min[i]));
+            b = fmaxf(b, __ldcg(&mp.sc->part_max[i]));
+        }
+        a = warp_min(a); b = warp_max(b);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) { shm[0][threadIdx.x >> 5] = a; shm[1][threadIdx.x >> 5] = b; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; ++w) { a = fminf(a, shm[0][w]); b = fmaxf(b, shm[1][w]); }
+            mp.out_minmax[0] = a;
+            mp.out_minmax[1] = b;
+            mp.sc->counter = 0;
+        }
+    }
+}
+
+// d -= d.min(); d /= d.max(); d = d * 2 - 1   with a rounding to T after every op
+template <typename T>
+__global__ void __launch_bounds__(256) renorm_kernel(T* d, long long n, const float* minmax) {
+    const float mn = minmax[0];
+    const float mx1 = Cvt<T>::round(__fsub_rn(minmax[1], mn));  // max of the shifted tensor (rounding is monotone)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float v = Cvt<T>::to_f(d[i]);
+        v = Cvt<T>::round(__fsub_rn(v, mn));
+        v = Cvt<T>::round(__fdiv_rn(v, mx1));
+        v = Cvt<T>::round(__fmul_rn(v, 2.0f));
+        v = Cvt<T>::round(__fsub_rn(v, 1.0f));
+        d[i] = Cvt<T>::from_f(v);
+    }
+}
+
+// =============================================================================================
+// host side
+// =============================================================================================
+static int check_problem(const rd_coalign_problem* p) {
+    RD_CHECK_ARG(p != nullptr, "problem is NULL");
+    RD_CHECK_ARG(p->G >= 1 && p->G <= RD_MAX_GROUPS, "G=%d out of range [1,%d]", p->G, RD_MAX_GROUPS);
+    RD_CHECK_ARG(p->w >= 1 && p->w <= RD_MAX_WINDOW, "w=%d out of range [1,%d]", p->w, RD_MAX_WINDOW);
+    RD_CHECK_ARG(p->N >= 1 && p->H >= 1 && p->W >= 1, "bad N/H/W");
+    RD_CHECK_ARG(p->dtype >= RD_F32 && p->dtype <= RD_BF16, "bad dtype %d", p->dtype);
+    RD_CHECK_ARG(p->n_total > 0 && p->P > 0 && p->P_pad >= p->P, "problem not initialised (call rd_coalign_problem_init)");
+    return RD_OK;
+}
+
+struct WsLayout {
+    size_t theta, gterm_local, gterm_global, part, counter, hist_frame, flags, total;
+    int C, steps_per_frame, RM, NV;
+};
+
+static int pick_rm(int R) {
+    const int opts[] = {4, 6, 9, 12, 16};
+    for (int o : opts)
+        if (R <= o) return o;
+    return -1;
+}
+
+static WsLayout ws_layout(const rd_coalign_problem* p, int n_iter) {
+    WsLayout L{};
+    const int R = p->G * p->w;
+    L.RM = pick_rm(R);
+    L.NV = 4 * (L.RM < 0 ? 16 : L.RM) + kFrameStats;
+    L.steps_per_frame = (p->P + kPassThreads * kPassV - 1) / (kPassThreads * kPassV);
+    L.C = (L.steps_per_frame + kPassItersPerChunk - 1) / kPassItersPerChunk;
+    if (L.C < 1) L.C = 1;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
+    L.theta = take(sizeof(float) * 2 * 6 * (size_t)p->n_total);
+    L.gterm_local = take(sizeof(float) * 2 * (size_t)p->N * R * 2);
+    L.gterm_global = take(sizeof(float) * 2 * (size_t)p->N * R * 2);
+    L.part = take(sizeof(float) * (size_t)p->N * L.C * L.NV);
+    L.counter = take(sizeof(unsigned) * (size_t)p->N);
+    L.hist_frame = take(sizeof(float) * (size_t)(n_iter > 0 ? n_iter : 1) * p->N * 4);
+    L.flags = take(256);
+    L.total = off;
+    return L;
+}
+
+struct WsFlags { int single_rank; int n_iter; };
+
+template <typename T>
+static int launch_pass_t(const PassParams& pp, int RM, dim3 grid, cudaStream_t st) {
+    switch (RM) {
+        case 4:  coalign_pass_kernel<T, 4><<<grid, kPassThreads, 0, st>>>(pp); break;
+        case 6:  coalign_pass_kernel<T, 6><<<grid, kPassThreads, 0, st>>>(pp); break;
+        case 9:  coalign_pass_kernel<T, 9><<<grid, kPassThreads, 0, st>>>(pp); break;
+        case 12: coalign_pass_kernel<T, 12><<<grid, kPassThreads, 0, st>>>(pp); break;
+        case 16: coalign_pass_kernel<T, 16><<<grid, kPassThreads, 0, st>>>(pp); break;
+        default: set_error("unsupported G*w"); return RD_ERR_UNSUPPORTED;
+    }
+    RD_LAUNCH_CHECK("coalign_pass_kernel");
+    return RD_OK;
+}
+
+static void fill_pass_params(PassParams& pp, const rd_coalign_problem* p, const rd_coalign_hparams* hp, const WsLayout& L,
+                             char* ws, int it, int step, bool single) {
+    const int R = p->G * p->w;
+    pp.G = p->G; pp.w = p->w; pp.N = p->N; pp.P = p->P; pp.P_pad = p->P_pad; pp.R = R; pp.C = L.C;
+    pp.n_total = p->n_total; pp.steps_per_frame = L.steps_per_frame;
+    for (int g = 0; g < RD_MAX_GROUPS; ++g) { pp.d[g] = p->d[g]; pp.n[g] = p->n[g]; pp.row0[g] = p->row0[g]; }
+    pp.apply_update = it > 0;
+    // torch.optim.Adam: python-double bias corrections, then fp32 tensor math
+    const double b1 = hp->beta1, b2 = hp->beta2;
+    const double k = (double)step;  // the update applied here is update number `step`
+    pp.step_size = (float)((double)hp->lr / (1.0 - pow(b1, k > 0 ? k : 1.0)));
+    pp.bc2_sqrt = (float)sqrt(1.0 - pow(b2, k > 0 ? k : 1.0));
+    pp.beta1 = hp->beta1; pp.beta2 = hp->beta2; pp.eps = hp->eps;
+    pp.lmda2 = hp->lmda2; pp.lmda3 = hp->lmda3; pp.dlw = hp->depth_loss_weight;
+    const double Z = (double)R * (double)p->N * (double)p->P;
+    pp.ls_over_Z = (float)((double)hp->loss_scale / Z);
+    pp.inv_P = (float)(1.0 / (double)p->P);
+    float* theta = reinterpret_cast<float*>(ws + L.theta);
+    const size_t th = 6 * (size_t)p->n_total;
+    // theta[(it-1)&1] holds theta_{it-1}; pass it writes theta_it to theta[it&1]; pass 0 reads theta[0]
+    pp.theta_in = theta + (it > 0 ? ((it - 1) & 1) : 0) * th;
+    pp.theta_out = theta + (it & 1) * th;
+    const size_t gt = (size_t)p->N * R * 2;
+    float* gl = reinterpret_cast<float*>(ws + L.gterm_local);
+    float* gg = single ? gl : reinterpret_cast<float*>(ws + L.gterm_global);
+    pp.gterm_in = gg + ((it > 0 ? it - 1 : 0) & 1) * gt;
+    pp.gterm_out = gl + (it & 1) * gt;
+    pp.part = reinterpret_cast<float*>(ws + L.part);
+    pp.counter = reinterpret_cast<unsigned*>(ws + L.counter);
+    pp.hist_frame = reinterpret_cast<float*>(ws + L.hist_frame) + (size_t)it * p->N * 4;
+}
+
+}  // namespace rd
+
+using namespace rd;
+
+extern "C" {
+
+int rd_coalign_problem_init(rd_coalign_problem* p) {
+    RD_CHECK_ARG(p != nullptr, "problem is NULL");
+    RD_CHECK_ARG(p->G >= 1 && p->G <= RD_MAX_GROUPS, "G=%d out of range [1,%d]", p->G, RD_MAX_GROUPS);
+    RD_CHECK_ARG(p->w >= 1 && p->w <= RD_MAX_WINDOW, "w=%d out of range [1,%d]", p->w, RD_MAX_WINDOW);
+    RD_CHECK_ARG(p->N >= 1 && p->H >= 1 && p->W >= 1, "bad N/H/W (%d,%d,%d)", p->N, p->H, p->W);
+    RD_CHECK_ARG(p->factor >= 1, "factor must be >= 1");
+    // the reference slices [border:-border]; border == 0 would give an empty tensor there
+    RD_CHECK_ARG(p->border >= 1, "border must be >= 1 (the reference's [border:-border] slice is empty for 0)");
+    RD_CHECK_ARG(p->H > 2 * p->border && p->W > 2 * p->border, "frame smaller than the border crop");
+    int row = 0;
+    for (int g = 0; g < p->G; ++g) {
+        RD_CHECK_ARG(p->d[g] >= 1, "dilation[%d]=%d must be >= 1", g, p->d[g]);
+        p->n[g] = p->N - (p->w - 1) * p->d[g];
+        RD_CHECK_ARG(p->n[g] >= 1, "dilation %d too large for %d frames with window %d", p->d[g], p->N, p->w);
+        p->row0[g] = row;
+        row += p->n[g];
+    }
+    for (int g = p->G; g < RD_MAX_GROUPS; ++g) { p->d[g] = 1; p->n[g] = 0; p->row0[g] = row; }
+    p->n_total = row;
+    p->Hs = (p->H - 2 * p->border + p->factor - 1) / p->factor;
+    p->Ws = (p->W - 2 * p->border + p->factor - 1) / p->factor;
+    p->P = p->Hs * p->Ws;
+    p->P_pad = (p->P + 7) & ~7;
+    return RD_OK;
+}
+
+int64_t rd_reduce_scratch_bytes(void) { return (int64_t)sizeof(RedScratch); }
+
+int rd_global_min(const void* const* host_snip_ptrs, const rd_coalign_problem* p, float* out_min, void* scratch,
+                  void* stream) {
+    if (int e = check_problem(p)) return e;
+    RD_CHECK_ARG(host_snip_ptrs && out_min && scratch, "NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    SegList segs{};
+    segs.nseg = p->G;
+    long long total = 0;
+    const size_t es = p->dtype == RD_F32 ? 4 : 2;
+    for (int g = 0; g < p->G; ++g) {
+        RD_CHECK_ARG(host_snip_ptrs[g] != nullptr, "snippet pointer %d is NULL", g);
+        RD_CHECK_ARG((reinterpret_cast<uintptr_t>(host_snip_ptrs[g]) % es) == 0, "snippet pointer %d misaligned", g);
+        segs.ptr[g] = host_snip_ptrs[g];
+        segs.count[g] = (long long)p->n[g] * p->w * p->H * p->W;
+        total += segs.count[g];
+    }
+    RedScratch* sc = reinterpret_cast<RedScratch*>(scratch);
+    RD_CUDA(cudaMemsetAsync(&sc->counter, 0, sizeof(unsigned), st));
+    long long want = (total / (16 / (long long)es) + 256 * 8 - 1) / (256 * 8);
+    int blocks = (int)(want < 1 ? 1 : (want > num_sms() * 8 ? num_sms() * 8 : want));
+    if (blocks > kRedMaxBlocks) blocks = kRedMaxBlocks;
+    switch (p->dtype) {
+        case RD_F32: global_min_kernel<float><<<blocks, 256, 0, st>>>(segs, sc, out_min); break;
+        case RD_F16: global_min_kernel<__half><<<blocks, 256, 0, st>>>(segs, sc, out_min); break;
+        default:     global_min_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(segs, sc, out_min); break;
+    }
+    RD_LAUNCH_CHECK("global_min_kernel");
+    return RD_OK;
+}
+
+int rd_coalign_prep(const void* const* host_snip_ptrs, const rd_coalign_problem* p, const float* dev_min,
+                    void* x_small, void* stream) {
+    if (int e = check_problem(p)) return e;
+    RD_CHECK_ARG(host_snip_ptrs && dev_min && x_small, "NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    PrepParams pp{};
+    pp.pb = *p;
+    for (int g = 0; g < p->G; ++g) {
+        RD_CHECK_ARG(host_snip_ptrs[g] != nullptr, "snippet pointer %d is NULL", g);
+        pp.snip[g] = host_snip_ptrs[g];
+    }
+    const long long total = (long long)p->n_total * p->w * p->P_pad;
+    long long want = (total + 255) / 256;
+    const int blocks = (int)(want > num_sms() * 16 ? num_sms() * 16 : want);
+    switch (p->dtype) {
+        case RD_F32: prep_kernel<float><<<blocks, 256, 0, st>>>(pp, dev_min, (float*)x_small); break;
+        case RD_F16: prep_kernel<__half><<<blocks, 256, 0, st>>>(pp, dev_min, (__half*)x_small); break;
+        default:     prep_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(pp, dev_min, (__nv_bfloat16*)x_small); break;
+    }
+    RD_LAUNCH_CHECK("prep_kernel");
+    return RD_OK;
+}
+
+int64_t rd_coalign_workspace_bytes(const rd_coalign_problem* p, int n_iter) {
+    if (check_problem(p) != RD_OK) return RD_ERR_BAD_ARG;
+    return (int64_t)ws_layout(p, n_iter).total;
+}
+
+int rd_coalign_begin(const rd_coalign_problem* p, const float* s, const float* t, const float* m_s, const float* m_t,
+                     const float* v_s, const float* v_t, int n_iter, int single_rank, void* workspace,
+                     int64_t workspace_bytes, void* stream) {
+    if (int e = check_problem(p)) return e;
+    RD_CHECK_ARG(s && t && m_s && m_t && v_s && v_t && workspace, "NULL pointer");
+    RD_CHECK_ARG(n_iter >= 0, "n_iter < 0");
+    const WsLayout L = ws_layout(p, n_iter);
+    if (L.RM < 0) { set_error("G*w = %d > 16 is not instantiated", p->G * p->w); return RD_ERR_UNSUPPORTED; }
+    if ((int64_t)L.total > workspace_bytes) {
+        set_error("workspace too small: need %lld bytes, got %lld", (long long)L.total, (long long)workspace_bytes);
+        return RD_ERR_WORKSPACE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = reinterpret_cast<char*>(workspace);
+    float* theta = reinterpret_cast<float*>(ws + L.theta);
+    const size_t nt = (size_t)p->n_total, b = nt * sizeof(float);
+    const float* src[6] = {s, t, m_s, m_t, v_s, v_t};
+    for (int i = 0; i < 6; ++i) RD_CUDA(cudaMemcpyAsync(theta + i * nt, src[i], b, cudaMemcpyDeviceToDevice, st));
+    RD_CUDA(cudaMemsetAsync(ws + L.gterm_local, 0, L.part - L.gterm_local, st));   // both gterm buffers
+    RD_CUDA(cudaMemsetAsync(ws + L.counter, 0, sizeof(unsigned) * (size_t)p->N, st));
+    RD_CUDA(cudaMemsetAsync(ws + L.hist_frame, 0, sizeof(float) * (size_t)(n_iter > 0 ? n_iter : 1) * p->N * 4, st));
+    WsFlags fl{single_rank, n_iter};
+    RD_CUDA(cudaMemcpyAsync(ws + L.flags, &fl, sizeof(fl), cudaMemcpyHostToDevice, st));
+    return RD_OK;
+}
+
+static int pass_impl(const void* x_small, const rd_coalign_problem* p, const rd_coalign_hparams* hp, int it, int step0,
+                     int f_begin, int f_end, void* workspace, void* stream, bool single, int n_iter_layout) {
+    const WsLayout L = ws_layout(p, n_iter_layout);
+    PassParams pp{};
+    pp.x = x_small;
+    pp.f_begin = f_begin;
+    fill_pass_params(pp, p, hp, L, reinterpret_cast<char*>(workspace), it, step0 + it, single);
+    dim3 grid(L.C, f_end - f_begin);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (p->dtype) {
+        case RD_F32: return launch_pass_t<float>(pp, L.RM, grid, st);
+        case RD_F16: return launch_pass_t<__half>(pp, L.RM, grid, st);
+        default:     return launch_pass_t<__nv_bfloat16>(pp, L.RM, grid, st);
+    }
+}
+
+// n_iter used for the layout is irrelevant for every offset except the (last) flags block, which the
+// pass does not touch, so the pass entry point does not need it.
+int rd_coalign_pass(const void* x_small, const rd_coalign_problem* p, const rd_coalign_hparams* hp, int it, int step0,
+                    int f_begin, int f_end, void* workspace, void* stream) {
+    if (int e = check_problem(p)) return e;
+    RD_CHECK_ARG(x_small && hp && workspace, "NULL pointer");
+    RD_CHECK_ARG(it >= 0 && 0 <= f_begin && f_begin < f_end && f_end <= p->N, "bad it / frame range [%d,%d)", f_begin, f_end);
+    const bool single = (f_begin == 0 && f_end == p->N);
+    return pass_impl(x_small, p, hp, it, step0, f_begin, f_end, workspace, stream, single, 1);
+}
+
+int rd_coalign_exchange(const rd_coalign_problem* p, void* workspace, int it, float** send, float** recv,
+                        int64_t* n_floats) {
+    if (int e = check_problem(p)) return e;
+    RD_CHECK_ARG(workspace && send && recv && n_floats, "NULL pointer");
+    const WsLayout L = ws_layout(p, 1);
+    const size_t gt = (size_t)p->N * p->G * p->w * 2;
+    char* ws = reinterpret_cast<char*>(workspace);
+    *send = reinterpret_cast<float*>(ws + L.gterm_local) + (it & 1) * gt;
+    *recv = reinterpret_cast<float*>(ws + L.gterm_global) + (it & 1) * gt;
+    *n_floats = (int64_t)gt;
+    return RD_OK;
+}
+
+int rd_coalign_end(const rd_coalign_problem* p, const rd_coalign_hparams* hp, int n_iter, int step0, int f_begin,
+                   int f_end, float* s, float* t, float* m_s, float* m_t, float* v_s, float* v_t, float* history,
+                   void* workspace, void* stream) {
+    if (int e = check_problem(p)) return e;
+    RD_CHECK_ARG(hp && s && t && m_s && m_t && v_s && v_t && workspace, "NULL pointer");
+    RD_CHECK_ARG(n_iter >= 0 && 0 <= f_begin && f_begin < f_end && f_end <= p->N, "bad n_iter / frame range");
+    const WsLayout L = ws_layout(p, n_iter);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool single = (f_begin == 0 && f_end == p->N);
+    PassParams pp{};
+    // "pass n_iter" would apply update number step0 + n_iter from the terms of pass n_iter - 1
+    fill_pass_params(pp, p, hp, L, reinterpret_cast<char*>(workspace), n_iter, step0 + n_iter, single);
+    coalign_final_update_kernel<<<(p->n_total + 127) / 128, 128, 0, st>>>(pp, f_begin, f_end, s, t, m_s, m_t, v_s, v_t);
+    RD_LAUNCH_CHECK("coalign_final_update_kernel");
+    if (n_iter > 0 && history != nullptr) {
+        coalign_history_kernel<<<n_iter, 256, 0, st>>>(reinterpret_cast<const float*>((char*)workspace + L.hist_frame),
+                                                       p->N, f_begin, f_end, history);
+        RD_LAUNCH_CHECK("coalign_history_kernel");
+    }
+    return RD_OK;
+}
+
+int rd_coalign_optimize(const void* x_small, const rd_coalign_problem* p, const rd_coalign_hparams* hp, float* s,
+                        float* t, float* m_s, float* m_t, float* v_s, float* v_t, int step0, int n_iter,
+                        float* history, void* workspace, int64_t workspace_bytes, void* stream) {
+    if (int e = check_problem(p)) return e;
+    RD_CHECK_ARG(x_small && hp, "NULL pointer");
+    if (int e = rd_coalign_begin(p, s, t, m_s, m_t, v_s, v_t, n_iter, 1, workspace, workspace_bytes, stream)) return e;
+    for (int it = 0; it < n_iter; ++it) {
+        if (int e = pass_impl(x_small, p, hp, it, step0, 0, p->N, workspace, stream, true, n_iter)) return e;
+    }
+    return rd_coalign_end(p, hp, n_iter, step0, 0, p->N, s, t, m_s, m_t, v_s, v_t, history, workspace, stream);
+}
+
+int rd_merge(const void* const* host_snip_ptrs, const rd_coalign_problem* p, const float* dev_min, const float* s,
+             const float* t, void* merged, float* out_minmax, void* scratch, void* stream) {
+    if (int e = check_problem(p)) return e;
+    RD_CHECK_ARG(host_snip_ptrs && dev_min && s && t && merged && out_minmax && scratch, "NULL pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    MergeParams mp{};
+    mp.pb = *p;
+    const size_t es = p->dtype == RD_F32 ? 4 : 2;
+    const long long HW = (long long)p->H * p->W;
+    for (int g = 0; g < p->G; ++g) {
+        RD_CHECK_ARG(host_snip_ptrs[g] != nullptr, "snippet pointer %d is NULL", g);
+        RD_CHECK_ARG((reinterpret_cast<uintptr_t>(host_snip_ptrs[g]) & 15) == 0, "snippet pointer %d must be 16-byte aligned", g);
+        mp.snip[g] = host_snip_ptrs[g];
+    }
+    RD_CHECK_ARG((reinterpret_cast<uintptr_t>(merged) & 15) == 0, "merged must be 16-byte aligned");
+    RD_CHECK_ARG((HW * (long long)es) % 16 == 0, "H*W*sizeof must be a multiple of 16 bytes (got H=%d W=%d)", p->H, p->W);
+    mp.s = s; mp.t = t; mp.dev_min = dev_min; mp.out = merged;
+    mp.sc = reinterpret_cast<RedScratch*>(scratch);
+    mp.out_minmax = out_minmax;
+    RD_CUDA(cudaMemsetAsync(&mp.sc->counter, 0, sizeof(unsigned), st));
+    const long long nvec = HW / (16 / (long long)es);
+    int bpf = (int)((nvec + 256 * 2 - 1) / (256 * 2));   // ~2 vectors per thread
+    if (bpf < 1) bpf = 1;
+    RD_CHECK_ARG(p->N <= kRedMaxBlocks, "too many frames for one merge launch (N=%d > %d)", p->N, kRedMaxBlocks);
+    while ((long long)bpf * p->N > kRedMaxBlocks && bpf > 1) bpf = (bpf + 1) / 2;
+    if ((long long)bpf * p->N > kRedMaxBlocks) bpf = 1;
+    mp.blocks_per_frame = bpf;
+    dim3 grid(bpf, p->N);
+    switch (p->dtype) {
+        case RD_F32: merge_kernel<float><<<grid, 256, 0, st>>>(mp); break;
+        case RD_F16: merge_kernel<__half><<<grid, 256, 0, st>>>(mp); break;
+        default:     merge_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(mp); break;
+    }
+    RD_LAUNCH_CHECK("merge_kernel");
+    return RD_OK;
+}
+
+int rd_renorm(void* depth, int64_t n, const float* dev_minmax, rd_dtype dtype, void* stream) {
+    RD_CHECK_ARG(depth && dev_minmax && n > 0, "bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    long long want = (n + 256 * 4 - 1) / (256 * 4);
+    const int blocks = (int)(want > num_sms() * 16 ? num_sms() * 16 : want);
+    switch (dtype) {
+        case RD_F32: renorm_kernel<float><<<blocks, 256, 0, st>>>((float*)depth, n, dev_minmax); break;
+        case RD_F16: renorm_kernel<__half><<<blocks, 256, 0, st>>>((__half*)depth, n, dev_minmax); break;
+        case RD_BF16: renorm_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((__nv_bfloat16*)depth, n, dev_minmax); break;
+        default: set_error("bad dtype"); return RD_ERR_BAD_ARG;
+    }
+    RD_LAUNCH_CHECK("renorm_kernel");
+    return RD_OK;
+}
+
+}  // extern "C"

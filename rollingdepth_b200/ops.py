@@ -1,0 +1,87 @@
+"""Functional wrappers over the C ABI (include/rd_b200.h) taking torch CUDA tensors.
+
+PyTorch is used for device memory and streams only; all arithmetic happens in librd_b200.so.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+
+def xattn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: Optional[float] = None,
+              out: Optional[torch.Tensor] = None, flags: int = 0) -> torch.Tensor:
+    """softmax(scale * q k^T) v over [B, S, H, D] views (any batch/seq/head strides, D contiguous).
+
+    Replaces F.scaled_dot_product_attention at attention_processor.py:2251-2253 of the reference;
+    q/k/v are the `[B, S, H*D]` projections viewed as `[B, S, H, D]` -- no transpose copies.
+    """
+    L.require_cuda(q, k, v)
+    if q.dim() != 4 or k.dim() != 4 or v.dim() != 4:
+        raise L.RdError("xattn_fwd expects [B, S, H, D] tensors")
+    B, Sq, H, D = q.shape
+    Sk = k.shape[1]
+    if k.shape != (B, Sk, H, D) or v.shape != (B, Sk, H, D):
+        raise L.RdError(f"shape mismatch q{tuple(q.shape)} k{tuple(k.shape)} v{tuple(v.shape)}")
+    if not (q.dtype == k.dtype == v.dtype):
+        raise L.RdError("q, k, v must share a dtype")
+    if q.stride(3) != 1 or k.stride(3) != 1 or v.stride(3) != 1:
+        raise L.RdError("head_dim axis must be contiguous")
+    if out is None:
+        out = torch.empty((B, Sq, H, D), dtype=q.dtype, device=q.device)
+    scale = (1.0 / math.sqrt(D)) if scale is None else float(scale)
+    code = L.lib().rd_xattn_fwd(
+        L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(out), B, H, Sq, Sk, D,
+        q.stride(0), q.stride(1), q.stride(2),
+        k.stride(0), k.stride(1), k.stride(2),
+        v.stride(0), v.stride(1), v.stride(2),
+        out.stride(0), out.stride(1), out.stride(2),
+        L.dtype_code(q.dtype), scale, int(flags), L.stream_ptr(q.device))
+    L.check(code, "rd_xattn_fwd")
+    return out
+
+
+_PTYPE = {"epsilon": 0, "sample": 1, "v_prediction": 2}
+
+
+def ddim_step(model_output: torch.Tensor, sample: torch.Tensor, sqrt_alpha_t: float, sqrt_beta_t: float,
+              sqrt_alpha_prev: float, sqrt_one_minus_alpha_prev: float, prediction_type: str,
+              clip: float = 0.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One DDIM step (eta = 0) with the reference's op-by-op rounding (scheduling_ddim.py:342-468)."""
+    L.require_cuda(model_output, sample)
+    if model_output.shape != sample.shape or model_output.dtype != sample.dtype:
+        raise L.RdError("model_output and sample must match in shape and dtype")
+    mo, sm = model_output.contiguous(), sample.contiguous()
+    if out is None:
+        out = torch.empty_like(sm)
+    code = L.lib().rd_ddim_step(L.ptr(mo), L.ptr(sm), L.ptr(out), sm.numel(), sqrt_alpha_t, sqrt_beta_t,
+                                sqrt_alpha_prev, sqrt_one_minus_alpha_prev, _PTYPE[prediction_type], float(clip),
+                                L.dtype_code(sm.dtype), L.stream_ptr(sm.device))
+    L.check(code, "rd_ddim_step")
+    return out
+
+
+def ddim_add_noise(original: torch.Tensor, noise: torch.Tensor, sqrt_alpha_prod: float,
+                   sqrt_one_minus_alpha_prod: float) -> torch.Tensor:
+    """scheduling_ddim.py:471-495."""
+    L.require_cuda(original, noise)
+    x, n = original.contiguous(), noise.contiguous()
+    out = torch.empty_like(x)
+    code = L.lib().rd_ddim_add_noise(L.ptr(x), L.ptr(n), L.ptr(out), x.numel(), sqrt_alpha_prod,
+                                     sqrt_one_minus_alpha_prod, L.dtype_code(x.dtype), L.stream_ptr(x.device))
+    L.check(code, "rd_ddim_add_noise")
+    return out
+
+
+def renorm_(depth: torch.Tensor, minmax: torch.Tensor) -> torch.Tensor:
+    """In place d = ((d - mn) / (mx - mn)) * 2 - 1 (rollingdepth_pipeline.py:316-318)."""
+    L.require_cuda(depth, minmax)
+    if not depth.is_contiguous():
+        raise L.RdError("renorm_ needs a contiguous tensor")
+    code = L.lib().rd_renorm(L.ptr(depth), depth.numel(), L.ptr(minmax), L.dtype_code(depth.dtype),
+                             L.stream_ptr(depth.device))
+    L.check(code, "rd_renorm")
+    return depth

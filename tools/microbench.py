@@ -1,0 +1,149 @@
+"""Kernel microbenchmarks (BASELINE.json config 5): cross-frame attention sweep and the 1000-frame
+co-alignment problem.  Prints one JSON object per line; CUDA-event timing after warm-up.
+
+    python tools/microbench.py attn [--full]      python tools/microbench.py align [--iters 200]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+def time_cuda(fn, warmup=3, iters=10, flush=None):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
+
+
+def bench_attn(args):
+    from rollingdepth_b200 import ops
+    dev = torch.device("cuda:0")
+    hbm, tf_peak, src = peaks()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    cases = []
+    if args.full:
+        for res in (512, 768, 1024):
+            for n in (3, 4, 6, 8):
+                hw = (res // 8) ** 2
+                cases.append((f"{res}px n={n} L0", n * hw, 5))
+                cases.append((f"{res}px n={n} L1", n * hw // 4, 10))
+    cases += [("fast L0 (768x432 n=3)", 15552, 5), ("fast L1", 3888, 10), ("fast L2", 1008, 20), ("fast mid", 252, 20),
+              ("full L0 (1024x576 n=3)", 27648, 5), ("full L1", 6912, 10)]
+    for dtype in (torch.float16, torch.bfloat16):
+        for name, S, H in cases:
+            q = torch.randn(1, S, H * 64, device=dev, dtype=dtype).view(1, S, H, 64)
+            k = torch.randn(1, S, H * 64, device=dev, dtype=dtype).view(1, S, H, 64)
+            v = torch.randn(1, S, H * 64, device=dev, dtype=dtype).view(1, S, H, 64)
+            out = torch.empty_like(q)
+            flops = 4.0 * H * S * S * 64
+            for flags in args.flags:
+                med, best = time_cuda(lambda: ops.xattn_fwd(q, k, v, out=out, flags=flags), flush=flush)
+                rec = dict(bench="xattn", case=name, S=S, H=H, dtype=str(dtype), flags=flags, ms=med, ms_best=best,
+                           tflops=flops / med / 1e9, frac_of_peak=flops / med / 1e9 / tf_peak, peak=tf_peak, peak_src=src)
+                # comparator: torch SDPA (what the reference calls) on the same strided views
+                if flags == args.flags[0]:
+                    qt, kt, vt = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
+                    try:
+                        m2, _ = time_cuda(lambda: torch.nn.functional.scaled_dot_product_attention(qt, kt, vt), flush=flush)
+                        rec["torch_sdpa_ms"] = m2
+                        rec["torch_sdpa_tflops"] = flops / m2 / 1e9
+                    except Exception as e:  # noqa: BLE001
+                        rec["torch_sdpa_err"] = str(e)[:80]
+                print(json.dumps(rec), flush=True)
+
+
+def bench_align(args):
+    from rollingdepth_b200.depth_aligner import DepthAligner
+    from oracle.gen_golden import synth_snippets  # generator only (inputs), not a compute path
+    dev = torch.device("cuda:0")
+    hbm, tf_peak, src = peaks()
+    cfgs = [("1000f 768x432 [1,25] fp32", 1000, 432, 768, [1, 25], torch.float32),
+            ("1000f 768x432 [1,25] fp16", 1000, 432, 768, [1, 25], torch.float16),
+            ("1000f 1024x576 [1,10,25] fp32", 1000, 576, 1024, [1, 10, 25], torch.float32),
+            ("150f 768x432 [1,25] fp16", 150, 432, 768, [1, 25], torch.float16)]
+    import ctypes as C
+    from rollingdepth_b200 import _lib as L
+    for name, N, H, W, dil, dtype in cfgs:
+        if args.small and N > 200:
+            continue
+        al = DepthAligner(device=dev, num_iterations=args.iters)
+        # Build the subsampled problem directly on the device (full-resolution 1000-frame snippets would be
+        # 15-20 GB); the optimiser only ever sees x_small.  prep / min / merge are timed separately below.
+        pb = L.CoalignProblem()
+        pb.G, pb.w, pb.N, pb.H, pb.W, pb.border, pb.factor = len(dil), 3, N, H, W, 2, 10
+        for g_, d_ in enumerate(dil):
+            pb.d[g_] = d_
+        pb.dtype = L.dtype_code(dtype)
+        L.check(L.lib().rd_coalign_problem_init(C.byref(pb)), "init")
+        sn_small = synth_snippets(N, pb.Hs, pb.Ws, 3, dil, seed=0, dtype=dtype)
+        mn = min(float(s.min()) for s in sn_small)
+        x_small = torch.zeros(pb.n_total, 3, pb.P_pad, dtype=dtype, device=dev)
+        x_small[:, :, :pb.P] = torch.cat([(s - mn).reshape(s.shape[0], 3, -1) for s in sn_small]).to(dev)
+        state = al.new_state(pb)
+        al.optimize_state(pb, x_small, state, 0, 5)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        hist = al.optimize_state(pb, x_small, state, 5, args.iters)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        es = 4 if dtype == torch.float32 else 2
+        bytes_iter = pb.n_total * pb.w * pb.P * es
+        gbs = bytes_iter * args.iters / ms / 1e6
+        h = hist.cpu()
+        print(json.dumps(dict(bench="coalign", case=name, n_snip=pb.n_total, P=pb.P, iters=args.iters, ms_total=ms,
+                              us_per_iter=1e3 * ms / args.iters, MB_per_iter=bytes_iter / 1e6, GBs=gbs,
+                              frac_of_hbm=gbs / hbm, peak=hbm, peak_src=src, loss0=float(h[0, 0]), lossN=float(h[-1, 0]),
+                              fits_L2=bytes_iter < 126e6)), flush=True)
+    # merge / min / prep at full resolution (150 frames, fp16, fast preset)
+    N, H, W, dil, dtype = 150, 432, 768, [1, 25], torch.float16
+    al = DepthAligner(device=dev)
+    snips = [torch.rand(N - 2 * d, 3, 1, H, W, device=dev, dtype=dtype) for d in dil]
+    tot_bytes = sum(s.numel() for s in snips) * 2
+    pb, dsn, dev_min, x_small = al.prepare(snips, dil)
+    state = al.new_state(pb)
+    med, best = time_cuda(lambda: al.prepare(snips, dil))
+    print(json.dumps(dict(bench="min+prep", case="150f 768x432 fp16", ms=med, GBs=tot_bytes / med / 1e6, frac_of_hbm=tot_bytes / med / 1e6 / hbm)))
+    med, best = time_cuda(lambda: al.merge(pb, dsn, dev_min, state[0], state[1]))
+    mb = tot_bytes + N * H * W * 2
+    print(json.dumps(dict(bench="merge", case="150f 768x432 fp16", ms=med, GBs=mb / med / 1e6, frac_of_hbm=mb / med / 1e6 / hbm)))
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", choices=["attn", "align"])
+    ap.add_argument("--full", action="store_true")
+    ap.add_argument("--small", action="store_true")
+    ap.add_argument("--iters", type=int, default=200)
+    ap.add_argument("--flags", type=int, nargs="+", default=[0])
+    a = ap.parse_args()
+    (bench_attn if a.what == "attn" else bench_align)(a)
