@@ -50,6 +50,14 @@ class CoalignHParams(C.Structure):
 
 _lib: Optional[C.CDLL] = None
 
+# number of kernels of librd_b200.so launched through this binding (bench.py reports it as gpu_launches)
+LAUNCHES = 0
+
+
+def count_launches(n: int) -> None:
+    global LAUNCHES
+    LAUNCHES += n
+
 # name -> (restype, argtypes); every symbol include/rd_b200.h declares
 _I64, _I, _F, _P = C.c_int64, C.c_int, C.c_float, C.c_void_p
 _PP = C.POINTER(C.c_void_p)

@@ -30,6 +30,8 @@ from . import ops
 class B200XFrameAttnProcessor:
     def __init__(self, kernel_flags: int = 0):
         self.kernel_flags = int(kernel_flags)
+        # bench.py sets this to a list to collect (shape, start_event, end_event) per kernel launch
+        self.events = None
 
     def __call__(
         self,
@@ -98,7 +100,15 @@ class B200XFrameAttnProcessor:
             k4 = attn.norm_k(k4)
 
         # reference: F.scaled_dot_product_attention default scale 1/sqrt(head_dim) (:2251)
+        ev = self.events
+        if ev is not None:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e0.record()
         out = ops.xattn_fwd(q4, k4, v4, scale=None, flags=self.kernel_flags)
+        if ev is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            ev.append(((batch, q4.shape[1], k4.shape[1], heads), e0, e1))
         hidden_states = out.reshape(batch, -1, heads * head_dim).to(query.dtype)
 
         hidden_states = attn.to_out[0](hidden_states)

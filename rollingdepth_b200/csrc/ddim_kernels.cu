@@ -19,11 +19,12 @@ __global__ void __launch_bounds__(256) ddim_step_kernel(const T* __restrict__ mo
             x0 = Cvt<T>::round(__fsub_rn(Cvt<T>::round(__fmul_rn(sa, x)), Cvt<T>::round(__fmul_rn(sb, v))));
             eps = Cvt<T>::round(__fadd_rn(Cvt<T>::round(__fmul_rn(sa, v)), Cvt<T>::round(__fmul_rn(sb, x))));
         } else if (ptype == 0) {   // epsilon (:415-417)
-            x0 = Cvt<T>::round(__fdiv_rn(Cvt<T>::round(__fsub_rn(x, Cvt<T>::round(__fmul_rn(sb, v)))), sa));
+            // torch's CUDA true-divide by a host scalar multiplies by the fp32 reciprocal
+            x0 = Cvt<T>::round(__fmul_rn(Cvt<T>::round(__fsub_rn(x, Cvt<T>::round(__fmul_rn(sb, v)))), __frcp_rn(sa)));
             eps = v;
         } else {                   // sample (:418-420)
             x0 = v;
-            eps = Cvt<T>::round(__fdiv_rn(Cvt<T>::round(__fsub_rn(x, Cvt<T>::round(__fmul_rn(sa, x0)))), sb));
+            eps = Cvt<T>::round(__fmul_rn(Cvt<T>::round(__fsub_rn(x, Cvt<T>::round(__fmul_rn(sa, x0)))), __frcp_rn(sb)));
         }
         if (clip > 0.f) x0 = fminf(fmaxf(x0, -clip), clip);   // :433-436
         const float dir = Cvt<T>::round(__fmul_rn(sbp, eps));                            // :449

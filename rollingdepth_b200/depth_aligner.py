@@ -103,6 +103,7 @@ class DepthAligner:
         L.check(lib.rd_global_min(ptrs, C.byref(pb), L.ptr(dev_min), L.ptr(scratch), st), "rd_global_min")
         x_small = torch.empty((pb.n_total, pb.w, pb.P_pad), dtype=dt, device=dev)
         L.check(lib.rd_coalign_prep(ptrs, C.byref(pb), L.ptr(dev_min), L.ptr(x_small), st), "rd_coalign_prep")
+        L.count_launches(2)
         return pb, snips, dev_min, x_small
 
     def new_state(self, pb: L.CoalignProblem):
@@ -126,6 +127,7 @@ class DepthAligner:
         L.check(lib.rd_coalign_optimize(L.ptr(x_small), C.byref(pb), C.byref(hp), *[L.ptr(a) for a in state],
                                         int(step0), int(n_iter), L.ptr(hist), L.ptr(ws), ws_bytes, L.stream_ptr(dev)),
                 "rd_coalign_optimize")
+        L.count_launches(n_iter + 2)      # one fused pass per iteration + final update + history reduction
         return hist[:n_iter]
 
     def merge(self, pb: L.CoalignProblem, snips: Sequence[torch.Tensor], dev_min: torch.Tensor, s: torch.Tensor,
@@ -137,6 +139,7 @@ class DepthAligner:
         scratch = torch.empty(lib.rd_reduce_scratch_bytes(), dtype=torch.uint8, device=dev)
         L.check(lib.rd_merge(L.ptr_array(snips), C.byref(pb), L.ptr(dev_min), L.ptr(s), L.ptr(t), L.ptr(merged),
                              L.ptr(self.merged_minmax), L.ptr(scratch), L.stream_ptr(dev)), "rd_merge")
+        L.count_launches(1)
         return merged
 
     # ------------------------------------------------------------------ reference entry point

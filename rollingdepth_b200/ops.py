@@ -41,6 +41,7 @@ def xattn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: Optional
         out.stride(0), out.stride(1), out.stride(2),
         L.dtype_code(q.dtype), scale, int(flags), L.stream_ptr(q.device))
     L.check(code, "rd_xattn_fwd")
+    L.count_launches(1)
     return out
 
 
@@ -61,6 +62,7 @@ def ddim_step(model_output: torch.Tensor, sample: torch.Tensor, sqrt_alpha_t: fl
                                 sqrt_alpha_prev, sqrt_one_minus_alpha_prev, _PTYPE[prediction_type], float(clip),
                                 L.dtype_code(sm.dtype), L.stream_ptr(sm.device))
     L.check(code, "rd_ddim_step")
+    L.count_launches(1)
     return out
 
 
@@ -73,6 +75,7 @@ def ddim_add_noise(original: torch.Tensor, noise: torch.Tensor, sqrt_alpha_prod:
     code = L.lib().rd_ddim_add_noise(L.ptr(x), L.ptr(n), L.ptr(out), x.numel(), sqrt_alpha_prod,
                                      sqrt_one_minus_alpha_prod, L.dtype_code(x.dtype), L.stream_ptr(x.device))
     L.check(code, "rd_ddim_add_noise")
+    L.count_launches(1)
     return out
 
 
@@ -84,4 +87,5 @@ def renorm_(depth: torch.Tensor, minmax: torch.Tensor) -> torch.Tensor:
     code = L.lib().rd_renorm(L.ptr(depth), depth.numel(), L.ptr(minmax), L.dtype_code(depth.dtype),
                              L.stream_ptr(depth.device))
     L.check(code, "rd_renorm")
+    L.count_launches(1)
     return depth

@@ -1,0 +1,419 @@
+"""`RollingDepthPipeline` -- drop-in for the reference's pipeline on B200.
+
+Same `__call__` / `forward` signatures, same `RollingDepthOutput` fields and the same numerics as
+rollingdepth/rollingdepth_pipeline.py (cited per method); what changes is the mechanism:
+
+  * the UNet runs with `B200XFrameAttnProcessor` (hand-written tcgen05 kernel) installed on every
+    attention layer;
+  * snippets are denoised `snippet_batch` at a time in one UNet call (legal: the `num_view` rearrange is
+    per batch element) instead of one by one (:415-446);
+  * the DDIM algebra is one fused kernel per step with host-side schedule scalars (no per-step sync);
+  * co-alignment / merge / re-normalisation run in the fused kernels of `DepthAligner`;
+  * with `torch.distributed` initialised (one process per GPU) the snippet list of every dilation is
+    block-partitioned over the ranks ("snippet sharding"); NCCL carries only small tensors (rgb latents,
+    subsampled predictions, per-frame partial sums of the merge, refined latents).
+
+There is no CPU fallback: the pipeline must live on a CUDA device.
+"""
+from __future__ import annotations
+
+import logging
+from dataclasses import dataclass
+from os import PathLike
+from typing import Dict, List, Optional, Union
+
+import torch
+
+from . import _lib as L
+from . import ops
+from .attn_processor import B200XFrameAttnProcessor
+from .depth_aligner import DepthAligner
+from .scheduler import DDIMSchedule
+from .sharding import Shard
+
+
+@dataclass
+class RollingDepthOutput:
+    """rollingdepth_pipeline.py:44-49."""
+    input_rgb: torch.Tensor
+    depth_pred: torch.Tensor
+    snippet_ls: Union[None, List[torch.Tensor]]
+    depth_coaligned: Union[None, torch.Tensor]
+
+
+class RollingDepthPipeline:
+    rgb_latent_scale_factor = 0.18215
+    depth_latent_scale_factor = 0.18215
+    N_CHANNEL_PER_LATENT = 4
+
+    def __init__(self, unet, vae, scheduler, text_encoder=None, tokenizer=None, snippet_batch: int = 8,
+                 install_processor: bool = True):
+        self.unet = unet
+        self.vae = vae
+        self.scheduler = DDIMSchedule.from_scheduler(scheduler)
+        self.text_encoder = text_encoder
+        self.tokenizer = tokenizer
+        self.empty_text_embed: torch.Tensor = None  # type: ignore
+        self.snippet_batch = int(snippet_batch)
+        self.shard = Shard()            # single rank unless torch.distributed is initialised (see enable_sharding)
+        self.timings: Dict[str, float] = {}
+        if install_processor:
+            self.unet.set_attn_processor(B200XFrameAttnProcessor())
+        logging.debug(f"Pipeline initialized: {type(self)}")
+
+    # ------------------------------------------------------------------ DiffusionPipeline-like surface
+    def to(self, device=None, dtype=None):
+        for m in (self.unet, self.vae, self.text_encoder):
+            if m is not None:
+                m.to(device=device, dtype=dtype)
+        return self
+
+    @property
+    def device(self) -> torch.device:
+        return next(self.unet.parameters()).device
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return next(self.unet.parameters()).dtype
+
+    def enable_sharding(self, group=None) -> "RollingDepthPipeline":
+        """Shard snippets over the ranks of `group` (default: the world group)."""
+        self.shard = Shard.from_dist(group)
+        return self
+
+    # ------------------------------------------------------------------ __call__ (rollingdepth_pipeline.py:78-176)
+    @torch.no_grad()
+    def __call__(
+        self,
+        input_video_path: PathLike,
+        start_frame: int = 0,
+        frame_count: int = 0,
+        processing_res: int = 1024,
+        resample_method: str = "BILINEAR",
+        dilations: List[int] = [1, 25],
+        cap_dilation: bool = True,
+        snippet_lengths: List[int] = [3],
+        init_infer_steps: List[int] = [1],
+        strides: List[int] = [1],
+        coalign_kwargs: Union[Dict, None] = None,
+        refine_step: int = 0,
+        refine_snippet_len: int = 3,
+        refine_start_dilation: int = 6,
+        generator: Union[torch.Generator, None] = None,
+        verbose: bool = False,
+        max_vae_bs: int = 4,
+        unload_snippet: bool = False,
+        restore_res: bool = False,
+    ) -> RollingDepthOutput:
+        assert processing_res >= 0
+        if processing_res > 1024:
+            logging.warning(f"Procssing at high-resolution ({processing_res}) may lead to suboptimal accuracy.")
+        from .video_io import load_video_frames, resize_frames
+        input_frames, original_res = load_video_frames(
+            input_path=input_video_path, start_frame=start_frame, frame_count=frame_count,
+            processing_res=processing_res, resample_method=resample_method, verbose=verbose)
+        input_frames = input_frames[None]                       # "n c h w -> 1 n c h w"
+        logging.info(f"{input_frames.shape[1]} frames loaded from video {input_video_path}")
+        if restore_res and max(original_res) > 2048:
+            logging.warning(f"Resizing back to large resolution ({list(original_res)}) may result in significant memory usage.")
+        pipe_output = self.forward(
+            input_frames=input_frames, dilations=dilations, cap_dilation=cap_dilation,
+            snippet_lengths=snippet_lengths, init_infer_steps=init_infer_steps, strides=strides,
+            coalign_kwargs=coalign_kwargs, refine_step=refine_step, refine_snippet_len=refine_snippet_len,
+            refine_start_dilation=refine_start_dilation, verbose=verbose, generator=generator,
+            max_vae_bs=max_vae_bs, unload_snippet=unload_snippet)
+        if restore_res:
+            pipe_output.input_rgb = resize_frames(pipe_output.input_rgb, list(original_res), resample_method)
+            pipe_output.depth_pred = resize_frames(pipe_output.depth_pred, list(original_res), resample_method)
+        return pipe_output
+
+    def encode_empty_text(self):
+        """rollingdepth_pipeline.py:178-191."""
+        if self.tokenizer is None or self.text_encoder is None:
+            raise RuntimeError("no text encoder/tokenizer: set `pipe.empty_text_embed` ([1, 2, cross_attention_dim])")
+        text_inputs = self.tokenizer("", padding="do_not_pad", max_length=self.tokenizer.model_max_length,
+                                     truncation=True, return_tensors="pt")
+        ids = text_inputs.input_ids.to(self.text_encoder.device)
+        self.empty_text_embed = self.text_encoder(ids)[0].to(self.dtype)
+
+    # ------------------------------------------------------------------ forward (rollingdepth_pipeline.py:193-354)
+    @torch.no_grad()
+    def forward(
+        self,
+        input_frames: torch.Tensor,  # [1 N 3 H W]
+        dilations: List[int],
+        cap_dilation: bool,
+        snippet_lengths: List[int],
+        init_infer_steps: List[int],
+        strides: List[int],
+        coalign_kwargs: Union[Dict, None],
+        refine_step: int,
+        refine_snippet_len: int,
+        refine_start_dilation: int,
+        generator: Union[torch.Generator, None],
+        verbose: bool,
+        max_vae_bs: int,
+        unload_snippet: bool,
+    ) -> RollingDepthOutput:
+        # ----------------- Check settings (:213-258) -----------------
+        assert 1 in dilations, "dilations should include 1"
+        assert len(snippet_lengths) == len(set(snippet_lengths)), f"Repeated values found in {snippet_lengths = }"
+        if len(snippet_lengths) > 1:
+            assert len(snippet_lengths) == len(dilations), \
+                f"inconsistent lengths of window_size ({snippet_lengths}) and dilations ({dilations})"
+        else:
+            snippet_lengths = snippet_lengths * len(dilations)
+        if len(init_infer_steps) > 1:
+            assert len(init_infer_steps) == len(dilations), \
+                f"inconsistent lengths of init_infer_step ({init_infer_steps}) and dilations ({dilations})"
+        else:
+            init_infer_steps = init_infer_steps * len(dilations)
+        assert min(init_infer_steps) > 0, "Minimum inference step is 1"
+        if len(strides) > 1:
+            assert len(strides) == len(dilations), f"inconsistent lengths of strides ({strides}) and dilations ({dilations})"
+        else:
+            strides = strides * len(dilations)
+        if [1] * len(dilations) != strides:
+            raise NotImplementedError("Only implemented for stride 1")
+
+        seq_len = input_frames.shape[1]
+        if cap_dilation:
+            for i, dilation in enumerate(dilations):        # mutates the caller's list, as the reference does (Q6)
+                dilations[i] = self.cap_max_dilation(seq_len=seq_len, snippet_len=snippet_lengths[i],
+                                                     dilation=dilation, verbose=verbose)
+            refine_start_dilation = self.cap_max_dilation(seq_len=seq_len, snippet_len=refine_snippet_len,
+                                                          dilation=refine_start_dilation, verbose=verbose)
+
+        device = self.device
+        if device.type != "cuda":
+            raise L.RdError("RollingDepthPipeline (B200) must be on a CUDA device; there is no CPU fallback")
+        if input_frames.shape[0] != 1:
+            raise NotImplementedError("Layered inference is only implemented for B=1")
+
+        # ----------------- Initial prediction -----------------
+        input_frames = input_frames.to(self.dtype).to(device, non_blocking=True)      # :263
+        rgb_latent = self.encode_rgb(input_frames, max_batch_size=max_vae_bs, verbose=verbose, sharded=True)
+        if self.empty_text_embed is None:
+            self.encode_empty_text()
+        B, seq_len, _, h, w = rgb_latent.shape
+
+        # the same noise for every frame (:281-288)
+        # (a generator living on another device, e.g. a CPU generator for reproducing a CPU run, is honoured
+        #  by drawing there and copying; the reference requires generator.device == pipeline device)
+        noise_dev = generator.device if generator is not None else device
+        init_noise = torch.randn((B, 4, h, w), device=noise_dev, dtype=self.dtype, generator=generator).to(device)
+        if self.shard.world > 1:
+            self.shard.broadcast_(init_noise)
+        init_noise = init_noise[:, None].expand(B, seq_len, 4, h, w)
+
+        snippet_pred_ls = self.init_snippet_infer(
+            rgb_latent=rgb_latent, init_noise=init_noise, dilations=dilations, cap_dilation=cap_dilation,
+            snippet_lengths=snippet_lengths, init_infer_steps=init_infer_steps, strides=strides,
+            max_vae_bs=max_vae_bs, unload_snippet=unload_snippet, verbose=verbose)
+
+        # ----------------- Co-alignment (:304-318) -----------------
+        coalign_kwargs = {} if coalign_kwargs is None else coalign_kwargs
+        depth_aligner = DepthAligner(verbose=verbose, device=device, **coalign_kwargs)
+        if self.shard.world > 1:
+            from .sharding import sharded_coalign
+            depth_coaligned, scales, translations, loss_history, snippet_pred_ls = sharded_coalign(
+                depth_aligner, self.shard, snippet_pred_ls, dilations, seq_len, snippet_lengths[0])
+        else:
+            depth_coaligned, scales, translations, loss_history = depth_aligner.run(
+                snippet_ls=snippet_pred_ls, dilations=dilations)
+        self.last_alignment = (scales, translations, loss_history)
+        # d -= d.min(); d /= d.max(); d = d*2-1, min/max come fused out of the merge kernel
+        ops.renorm_(depth_coaligned, depth_aligner.merged_minmax)
+
+        # ----------------- Refinement (:322-345) -----------------
+        if refine_step > 0:
+            depth_latent_coaligned = self.encode_rgb(
+                depth_coaligned[None].expand(1, seq_len, 3, *depth_coaligned.shape[-2:]),   # "N 1 H W -> 1 N 3 H W"
+                max_batch_size=max_vae_bs, verbose=verbose, sharded=True)
+            depth_latent_new = self.refine(
+                rgb_latent=rgb_latent, depth_latents=depth_latent_coaligned, init_noise=init_noise,
+                refine_step=refine_step, snippet_len=refine_snippet_len, start_dilation=refine_start_dilation,
+                verbose=verbose)
+            depth_pred = self.decode_depth(depth_latent_new, max_batch_size=max_vae_bs, verbose=verbose, sharded=True)
+        else:
+            depth_pred = depth_coaligned
+
+        # ----------------- Output (:347-354) -----------------
+        return RollingDepthOutput(
+            input_rgb=input_frames.detach().cpu().squeeze(0) / 2.0 + 0.5,
+            depth_pred=depth_pred.detach().cpu().squeeze(0),
+            snippet_ls=[snippet.detach().cpu() for snippet in snippet_pred_ls],
+            depth_coaligned=depth_coaligned.detach().cpu().squeeze(0),
+        )
+
+    # ------------------------------------------------------------------ initial snippet inference (:356-463)
+    def init_snippet_infer(self, rgb_latent, init_noise, dilations, cap_dilation, snippet_lengths, init_infer_steps,
+                           strides, max_vae_bs, unload_snippet, verbose) -> List[torch.Tensor]:
+        B, seq_len, _, h, w = rgb_latent.shape
+        if 1 != B:
+            raise NotImplementedError("RollingDepth is implemented for B=1")
+        text = self.empty_text_embed.to(self.device)            # [1, 2, C]
+        snippet_pred_ls = []
+        for dilation, snippet_len, stride, init_infer_step in zip(dilations, snippet_lengths, strides, init_infer_steps):
+            timesteps = self.scheduler.set_timesteps(init_infer_step)
+            snippet_idx_ls = self.get_snippet_indice(
+                i_step=0, timesteps=timesteps, seq_len=seq_len, snippet_len=snippet_len,
+                dilation_start=dilation, dilation_end=dilation, stride=stride)
+            lo, hi = self.shard.block(len(snippet_idx_ls))      # this rank's contiguous block of snippets
+            mine = snippet_idx_ls[lo:hi]
+            latents = []
+            for b0 in range(0, len(mine), self.snippet_batch):
+                idx = torch.tensor(mine[b0:b0 + self.snippet_batch], device=self.device)      # [b, n]
+                rgb_snip = rgb_latent[0, idx]                     # [b, n, 4, h, w] (gather copy, :417)
+                depth_snip = init_noise[0, idx].contiguous()
+                for t in timesteps:
+                    pred = self.single_step(rgb_snip, depth_snip, t, text)
+                    depth_snip = self.scheduler.step(pred, t, depth_snip)
+                latents.append(depth_snip)
+            if latents:
+                depth_snippet_latent = torch.cat(latents, dim=0)  # [n_mine, n, 4, h, w]
+                decoded = self.decode_depth(depth_snippet_latent, max_batch_size=max_vae_bs, verbose=verbose)
+            else:
+                H, W = self._decoded_hw(h, w)
+                decoded = torch.empty((0, snippet_len, 1, H, W), device=self.device, dtype=self.dtype)
+            if unload_snippet:
+                decoded = decoded.cpu()
+            snippet_pred_ls.append(decoded)
+        return snippet_pred_ls
+
+    def _decoded_hw(self, h, w):
+        f = 2 ** (len(self.vae.decoder.up_blocks) - 1)
+        return h * f, w * f
+
+    @staticmethod
+    def get_snippet_indice(i_step: int, timesteps, seq_len: int, snippet_len: int, dilation_start: int,
+                           dilation_end: int, stride: int) -> List[List[int]]:
+        """rollingdepth_pipeline.py:465-502 (the annealing expression is float-rounding sensitive, Q12)."""
+        gap_start = dilation_start - 1
+        gap_end = dilation_end - 1
+        assert gap_start >= gap_end, f"expect gap_start > gap_end, but got {gap_start} and {gap_end}"
+        assert gap_start >= 0 and gap_end >= 0
+        total_step = len(timesteps)
+        gap_cur = int((1 - (i_step) / total_step) * (gap_start - gap_end) + gap_end)
+        total_window_size = (snippet_len - 1) * (gap_cur + 1) + 1
+        i_start_ls = list(range(0, seq_len - total_window_size + 1, stride))
+        if i_start_ls[-1] < seq_len - total_window_size:
+            i_start_ls.append(seq_len - total_window_size)
+        snippet_idx_ls = [list(range(i0, i0 + total_window_size, gap_cur + 1)) for i0 in i_start_ls]
+        if not set(range(0, seq_len)) == set([x for f in snippet_idx_ls for x in f]):
+            logging.warning("Not every frame is covered. Consider reducing dilation for short videos")
+        return snippet_idx_ls
+
+    @staticmethod
+    def cap_max_dilation(seq_len: int, snippet_len: int, dilation: int, verbose: bool):
+        """rollingdepth_pipeline.py:504-515."""
+        max_allowed_gap = int(seq_len / snippet_len) - 1
+        if max_allowed_gap < dilation:
+            msg = f"{dilation = } is too big for {seq_len} frames. Reduced to {max_allowed_gap}"
+            logging.info(msg) if verbose else logging.debug(msg)
+            dilation = min(max_allowed_gap, dilation)
+        return dilation
+
+    # ------------------------------------------------------------------ refinement (:517-633)
+    def refine(self, rgb_latent, depth_latents, init_noise, refine_step, snippet_len, start_dilation, verbose,
+               skip_t_ratio: float = 0.5) -> torch.Tensor:
+        B, seq_len, _, h, w = rgb_latent.shape
+        if 1 != B:
+            raise NotImplementedError("Layered inference is only implemented for B=1")
+        total_scheduler_step = int(refine_step / skip_t_ratio)
+        assert total_scheduler_step <= self.scheduler.num_train_timesteps, "Too many refinement steps"
+        timesteps = self.scheduler.set_timesteps(total_scheduler_step)
+        timesteps = timesteps[int(len(timesteps) * skip_t_ratio):]
+        assert 0 < len(timesteps) < total_scheduler_step, f"invalid {skip_t_ratio = }"
+
+        depth_latent_new = self.scheduler.add_noise(depth_latents, init_noise.contiguous(), timesteps[0])   # :548-552
+        text = self.empty_text_embed.to(self.device)
+
+        for i_step, t_current in enumerate(timesteps):
+            snippet_idx_ls = self.get_snippet_indice(
+                i_step=i_step, timesteps=timesteps, seq_len=seq_len, snippet_len=snippet_len,
+                dilation_start=start_dilation, dilation_end=1, stride=1)
+            n_win = len(snippet_idx_ls)
+            g = snippet_idx_ls[0][1] - snippet_idx_ls[0][0] if snippet_len > 1 else 1
+            depth_latent_old = depth_latent_new                     # every window reads the OLD latent (:605)
+            lo, hi = self.shard.block(n_win)
+            preds = torch.empty((n_win, snippet_len, 4, h, w), device=self.device, dtype=self.dtype)
+            for b0 in range(lo, hi, self.snippet_batch):
+                b1 = min(b0 + self.snippet_batch, hi)
+                idx = torch.tensor(snippet_idx_ls[b0:b1], device=self.device)
+                rgb_in = rgb_latent[0, idx]
+                depth_in = depth_latent_old[0, idx]
+                pred = self.single_step(rgb_in, depth_in, t_current, text)
+                self.scheduler.step(pred, t_current, depth_in, out=preds[b0:b1])
+            if self.shard.world > 1:
+                preds = self.shard.all_gather_blocks(preds, n_win)
+            # accumulate per frame in the reference's order (windows by ascending start => j = n-1 ... 0), with the
+            # reference's in-dtype rounding after every += (:621-624), then average by the integer count (:629)
+            new = torch.zeros_like(depth_latent_old[0])
+            count = torch.zeros(seq_len, device=self.device, dtype=torch.int32)
+            for j in range(snippet_len - 1, -1, -1):
+                new[j * g: j * g + n_win] += preds[:, j]
+                count[j * g: j * g + n_win] += 1
+            # coverage is pure index logic: check it on the host instead of syncing on `count` (:628)
+            assert (snippet_len - 1) * g + n_win == seq_len, "refinement windows do not cover every frame"
+            depth_latent_new = (new / count[:, None, None, None])[None]
+        return depth_latent_new
+
+    # ------------------------------------------------------------------ UNet step (:635-663)
+    def single_step(self, rgb_latent: torch.Tensor, depth_latent: torch.Tensor, timestep: int,
+                    encoder_hidden_states: torch.Tensor) -> torch.Tensor:
+        """rgb/depth latents [b, n, 4, h, w] (b snippets at once) -> model output [b, n, 4, h, w]."""
+        assert depth_latent.shape == rgb_latent.shape
+        b, n = rgb_latent.shape[:2]
+        unet_input = torch.cat([rgb_latent.flatten(0, 1), depth_latent.flatten(0, 1)], dim=1)   # [(b n), 8, h, w]
+        t_input = torch.full((b * n,), int(timestep), device=unet_input.device, dtype=torch.int64)
+        ctx = encoder_hidden_states
+        if ctx.shape[0] == 1 and b > 1:
+            ctx = ctx.expand(b, -1, -1)          # reference code with an expanded context runs batched (Q2)
+        noise_pred = self.unet(unet_input, t_input, encoder_hidden_states=ctx, num_view=n).sample
+        return noise_pred.unflatten(0, (b, n))
+
+    # ------------------------------------------------------------------ VAE wrappers (:665-740)
+    def encode_rgb(self, rgb_in: torch.Tensor, max_batch_size: int, verbose: bool = False, sharded: bool = False) -> torch.Tensor:
+        if 5 == rgb_in.dim():
+            B, N, _, H, W = rgb_in.shape
+        else:
+            B, _, H, W = rgb_in.shape
+            N = 1
+        flat = rgb_in.reshape(B * N, *rgb_in.shape[-3:])
+        lo, hi = self.shard.block(B * N) if sharded else (0, B * N)
+        latents = []
+        for i in range(lo, hi, max_batch_size):
+            batch = flat[i:min(i + max_batch_size, hi)]
+            moments = self.vae.quant_conv(self.vae.encoder(batch))
+            mean, _logvar = torch.chunk(moments, 2, dim=1)          # posterior mean, no sampling (Q11)
+            latents.append(mean)
+        lat = torch.cat(latents, dim=0) * self.rgb_latent_scale_factor if latents else None
+        if sharded and self.shard.world > 1:
+            h, w = self._latent_hw(H, W)
+            if lat is None:
+                lat = torch.empty((0, 4, h, w), device=self.device, dtype=self.dtype)
+            lat = self.shard.all_gather_blocks(lat, B * N)
+        return lat.unflatten(0, (B, N))
+
+    def _latent_hw(self, H, W):
+        with torch.no_grad():
+            f = 2 ** (len(self.vae.encoder.down_blocks) - 1)
+        return (H + f - 1) // f, (W + f - 1) // f
+
+    def decode_depth(self, depth_latent: torch.Tensor, max_batch_size: int, verbose: bool = False, sharded: bool = False) -> torch.Tensor:
+        B, N, C, H, W = depth_latent.shape
+        flat = depth_latent.flatten(0, 1) / self.depth_latent_scale_factor
+        lo, hi = self.shard.block(B * N) if sharded else (0, B * N)
+        outs = []
+        for i in range(lo, hi, max_batch_size):
+            batch = flat[i:min(i + max_batch_size, hi)]
+            stacked = self.vae.decoder(self.vae.post_quant_conv(batch))
+            outs.append(stacked.mean(dim=1, keepdim=True))          # mean over the 3 output channels (:737)
+        dec = torch.cat(outs, dim=0) if outs else None
+        if sharded and self.shard.world > 1:
+            if dec is None:
+                Hd, Wd = self._decoded_hw(H, W)
+                dec = torch.empty((0, 1, Hd, Wd), device=self.device, dtype=self.dtype)
+            dec = self.shard.all_gather_blocks(dec, B * N)
+        return dec.unflatten(0, (B, N))

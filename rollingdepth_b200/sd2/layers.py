@@ -1,0 +1,261 @@
+"""Building blocks of the SD2-architecture UNet / VAE that RollingDepth runs.
+
+These are the *callers* of the hot kernel: plain PyTorch modules whose
+convolutions, GEMMs and norms stay on cuDNN / cuBLAS, and whose `Attention` module exposes the same
+plug-in surface as diffusers' (`processor(attn, hidden_states, encoder_hidden_states=..., num_view=...)`,
+`set_processor`, `to_q/to_k/to_v/to_out`, `heads`, `scale`), so that `B200XFrameAttnProcessor` is a
+drop-in on either.  Parameter names and shapes match diffusers 0.30 so a `prs-eth/rollingdepth-v1-0`
+(or any SD2-layout) state dict loads with `strict=True`.
+
+Reference for behaviour: diffusers/src/diffusers/models/{attention_processor.py:45-716, attention.py:421-548,
+transformers/transformer_2d.py:327-483, resnet.py:200-376, downsampling.py, upsampling.py, embeddings.py}.
+"""
+from __future__ import annotations
+
+import inspect
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+# --------------------------------------------------------------------------- time embedding
+def timestep_embedding(timesteps: torch.Tensor, dim: int, flip_sin_to_cos: bool = True, freq_shift: float = 0.0,
+                       max_period: int = 10000) -> torch.Tensor:
+    """Sinusoidal embedding (embeddings.py get_timestep_embedding), fp32 math."""
+    half = dim // 2
+    exponent = -math.log(max_period) * torch.arange(0, half, dtype=torch.float32, device=timesteps.device)
+    exponent = exponent / (half - freq_shift)
+    emb = timesteps[:, None].float() * torch.exp(exponent)[None, :]
+    emb = torch.cat([torch.sin(emb), torch.cos(emb)], dim=-1)
+    if flip_sin_to_cos:
+        emb = torch.cat([emb[:, half:], emb[:, :half]], dim=-1)
+    if dim % 2 == 1:
+        emb = F.pad(emb, (0, 1, 0, 0))
+    return emb
+
+
+class TimestepEmbedding(nn.Module):
+    def __init__(self, in_channels: int, time_embed_dim: int):
+        super().__init__()
+        self.linear_1 = nn.Linear(in_channels, time_embed_dim)
+        self.act = nn.SiLU()
+        self.linear_2 = nn.Linear(time_embed_dim, time_embed_dim)
+
+    def forward(self, sample):
+        return self.linear_2(self.act(self.linear_1(sample)))
+
+
+# --------------------------------------------------------------------------- attention (plug-in surface)
+class TorchSDPAProcessor:
+    """Library attention (torch SDPA) with the reference's `num_view` semantics; used for the VAE
+    mid-block (1 head, head_dim 512 -- SURVEY K4, left on the library) and selectable for A/B runs."""
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, temb=None,
+                 num_view: int = None, *args, **kwargs):
+        residual = hidden_states
+        input_ndim = hidden_states.ndim
+        if input_ndim == 4:
+            b, c, h, w = hidden_states.shape
+            hidden_states = hidden_states.view(b, c, h * w).transpose(1, 2)
+        if num_view is not None:
+            bn, hw, c_ = hidden_states.shape
+            hidden_states = hidden_states.reshape(bn // num_view, num_view * hw, c_)
+        if attn.group_norm is not None:
+            hidden_states = attn.group_norm(hidden_states.transpose(1, 2)).transpose(1, 2)
+        query = attn.to_q(hidden_states)
+        ctx = hidden_states if encoder_hidden_states is None else encoder_hidden_states
+        if ctx.shape[0] != hidden_states.shape[0]:
+            ctx = ctx.expand(hidden_states.shape[0], -1, -1)
+        key, value = attn.to_k(ctx), attn.to_v(ctx)
+        batch = hidden_states.shape[0]
+        d = key.shape[-1] // attn.heads
+        q = query.view(batch, -1, attn.heads, d).transpose(1, 2)
+        k = key.view(batch, -1, attn.heads, d).transpose(1, 2)
+        v = value.view(batch, -1, attn.heads, d).transpose(1, 2)
+        o = F.scaled_dot_product_attention(q, k, v, dropout_p=0.0, is_causal=False)
+        o = o.transpose(1, 2).reshape(batch, -1, attn.heads * d).to(query.dtype)
+        o = attn.to_out[1](attn.to_out[0](o))
+        if num_view is not None:
+            b_, s_, c_ = o.shape
+            o = o.reshape(b_ * num_view, s_ // num_view, c_)
+        if input_ndim == 4:
+            o = o.transpose(-1, -2).reshape(b, c, h, w)
+        if attn.residual_connection:
+            o = o + residual
+        return o / attn.rescale_output_factor
+
+
+class Attention(nn.Module):
+    """Same attribute surface as diffusers' Attention (attention_processor.py:45-268)."""
+
+    def __init__(self, query_dim: int, cross_attention_dim: Optional[int] = None, heads: int = 8, dim_head: int = 64,
+                 bias: bool = False, out_bias: bool = True, norm_num_groups: Optional[int] = None, eps: float = 1e-5,
+                 residual_connection: bool = False, rescale_output_factor: float = 1.0, processor=None):
+        super().__init__()
+        self.inner_dim = dim_head * heads
+        self.query_dim = query_dim
+        self.is_cross_attention = cross_attention_dim is not None
+        self.cross_attention_dim = cross_attention_dim if cross_attention_dim is not None else query_dim
+        self.heads = heads
+        self.scale = dim_head ** -0.5
+        self.residual_connection = residual_connection
+        self.rescale_output_factor = rescale_output_factor
+        self.group_norm = nn.GroupNorm(norm_num_groups, query_dim, eps=eps, affine=True) if norm_num_groups else None
+        self.spatial_norm = None
+        self.norm_q = self.norm_k = None
+        self.norm_cross = None
+        self.to_q = nn.Linear(query_dim, self.inner_dim, bias=bias)
+        self.to_k = nn.Linear(self.cross_attention_dim, self.inner_dim, bias=bias)
+        self.to_v = nn.Linear(self.cross_attention_dim, self.inner_dim, bias=bias)
+        self.to_out = nn.ModuleList([nn.Linear(self.inner_dim, query_dim, bias=out_bias), nn.Dropout(0.0)])
+        self.processor = None
+        self.set_processor(processor if processor is not None else TorchSDPAProcessor())
+
+    def set_processor(self, processor) -> None:
+        self.processor = processor
+        self._proc_params = set(inspect.signature(processor.__call__).parameters.keys())
+
+    def get_processor(self):
+        return self.processor
+
+    def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **cross_attention_kwargs):
+        # diffusers filters kwargs by the processor's signature (attention_processor.py:483-492); a processor
+        # that does not declare `num_view` would silently fall back to per-frame attention -- refuse instead.
+        unknown = [k for k in cross_attention_kwargs if k not in self._proc_params]
+        if "num_view" in unknown and cross_attention_kwargs["num_view"] is not None:
+            raise TypeError(f"{type(self.processor).__name__} does not accept `num_view`")
+        kw = {k: v for k, v in cross_attention_kwargs.items() if k in self._proc_params}
+        return self.processor(self, hidden_states, encoder_hidden_states=encoder_hidden_states,
+                              attention_mask=attention_mask, **kw)
+
+
+class GEGLU(nn.Module):
+    def __init__(self, dim_in: int, dim_out: int):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+    def forward(self, x):
+        h, gate = self.proj(x).chunk(2, dim=-1)
+        return h * F.gelu(gate)
+
+
+class FeedForward(nn.Module):
+    def __init__(self, dim: int, mult: int = 4):
+        super().__init__()
+        self.net = nn.ModuleList([GEGLU(dim, dim * mult), nn.Dropout(0.0), nn.Linear(dim * mult, dim)])
+
+    def forward(self, x):
+        for m in self.net:
+            x = m(x)
+        return x
+
+
+class BasicTransformerBlock(nn.Module):
+    """attention.py:421-548 (layer_norm variant): LN -> attn1 (self, cross-frame) -> LN -> attn2 (text) -> LN -> GEGLU FF.
+    `num_view` goes to attn1 AND attn2, as in the reference (:467-475, :508-516)."""
+
+    def __init__(self, dim: int, heads: int, dim_head: int, cross_attention_dim: Optional[int]):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-5)
+        self.attn1 = Attention(dim, None, heads, dim_head)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-5)
+        self.attn2 = Attention(dim, cross_attention_dim, heads, dim_head)
+        self.norm3 = nn.LayerNorm(dim, eps=1e-5)
+        self.ff = FeedForward(dim)
+
+    def forward(self, x, encoder_hidden_states=None, num_view=None):
+        x = self.attn1(self.norm1(x), encoder_hidden_states=None, num_view=num_view) + x
+        x = self.attn2(self.norm2(x), encoder_hidden_states=encoder_hidden_states, num_view=num_view) + x
+        x = self.ff(self.norm3(x)) + x
+        return x
+
+
+class Transformer2DModel(nn.Module):
+    """transformers/transformer_2d.py:327-483, continuous-input path."""
+
+    def __init__(self, heads: int, dim_head: int, in_channels: int, num_layers: int = 1,
+                 cross_attention_dim: Optional[int] = None, norm_num_groups: int = 32, use_linear_projection: bool = True):
+        super().__init__()
+        inner = heads * dim_head
+        self.use_linear_projection = use_linear_projection
+        self.norm = nn.GroupNorm(norm_num_groups, in_channels, eps=1e-6, affine=True)
+        self.proj_in = nn.Linear(in_channels, inner) if use_linear_projection else nn.Conv2d(in_channels, inner, 1)
+        self.transformer_blocks = nn.ModuleList(
+            [BasicTransformerBlock(inner, heads, dim_head, cross_attention_dim) for _ in range(num_layers)])
+        self.proj_out = nn.Linear(inner, in_channels) if use_linear_projection else nn.Conv2d(inner, in_channels, 1)
+
+    def forward(self, x, encoder_hidden_states=None, num_view=None):
+        b, c, h, w = x.shape
+        residual = x
+        x = self.norm(x)
+        if self.use_linear_projection:
+            x = x.permute(0, 2, 3, 1).reshape(b, h * w, c)
+            x = self.proj_in(x)
+        else:
+            x = self.proj_in(x)
+            x = x.permute(0, 2, 3, 1).reshape(b, h * w, x.shape[1])
+        for blk in self.transformer_blocks:
+            x = blk(x, encoder_hidden_states=encoder_hidden_states, num_view=num_view)
+        if self.use_linear_projection:
+            x = self.proj_out(x)
+            x = x.reshape(b, h, w, -1).permute(0, 3, 1, 2).contiguous()
+        else:
+            x = x.reshape(b, h, w, -1).permute(0, 3, 1, 2).contiguous()
+            x = self.proj_out(x)
+        return x + residual
+
+
+# --------------------------------------------------------------------------- conv blocks
+class ResnetBlock2D(nn.Module):
+    """resnet.py:200-376, default time-scale-shift, swish."""
+
+    def __init__(self, in_channels: int, out_channels: int, temb_channels: Optional[int], groups: int = 32,
+                 eps: float = 1e-5, output_scale_factor: float = 1.0):
+        super().__init__()
+        self.norm1 = nn.GroupNorm(groups, in_channels, eps=eps, affine=True)
+        self.conv1 = nn.Conv2d(in_channels, out_channels, 3, padding=1)
+        self.time_emb_proj = nn.Linear(temb_channels, out_channels) if temb_channels is not None else None
+        self.norm2 = nn.GroupNorm(groups, out_channels, eps=eps, affine=True)
+        self.dropout = nn.Dropout(0.0)
+        self.conv2 = nn.Conv2d(out_channels, out_channels, 3, padding=1)
+        self.nonlinearity = nn.SiLU()
+        self.conv_shortcut = nn.Conv2d(in_channels, out_channels, 1) if in_channels != out_channels else None
+        self.output_scale_factor = output_scale_factor
+
+    def forward(self, x, temb=None):
+        h = self.conv1(self.nonlinearity(self.norm1(x)))
+        if self.time_emb_proj is not None and temb is not None:
+            h = h + self.time_emb_proj(self.nonlinearity(temb))[:, :, None, None]
+        h = self.conv2(self.dropout(self.nonlinearity(self.norm2(h))))
+        if self.conv_shortcut is not None:
+            x = self.conv_shortcut(x)
+        out = x + h
+        return out if self.output_scale_factor == 1.0 else out / self.output_scale_factor
+
+
+class Downsample2D(nn.Module):
+    def __init__(self, channels: int, padding: int = 1):
+        super().__init__()
+        self.padding = padding
+        self.conv = nn.Conv2d(channels, channels, 3, stride=2, padding=padding)
+
+    def forward(self, x):
+        if self.padding == 0:
+            x = F.pad(x, (0, 1, 0, 1), mode="constant", value=0)
+        return self.conv(x)
+
+
+class Upsample2D(nn.Module):
+    def __init__(self, channels: int):
+        super().__init__()
+        self.conv = nn.Conv2d(channels, channels, 3, padding=1)
+
+    def forward(self, x, output_size=None):
+        if output_size is None:
+            x = F.interpolate(x, scale_factor=2.0, mode="nearest")
+        else:
+            x = F.interpolate(x, size=tuple(output_size), mode="nearest")
+        return self.conv(x)

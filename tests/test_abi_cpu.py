@@ -1,0 +1,130 @@
+"""CPU checks of the C-ABI boundary and of the host-side sharding logic (no GPU compute)."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "rd_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return set(re.findall(r"\b(rd_[a-z0-9_]+)\s*\(", src)) - {"rd_status", "rd_dtype"}
+
+
+def test_library_exports_every_declared_symbol():
+    from rollingdepth_b200 import _lib as L
+    from rollingdepth_b200 import build
+    build.build()
+    declared = _header_functions()
+    assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
+    lib = L.lib()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.rd_version() == 1
+
+
+def test_sass_contains_blackwell_instructions():
+    """The attention kernel must be a tcgen05/TMA kernel, not a recompiled mma.sync one."""
+    from rollingdepth_b200 import build
+    lib = build.build()
+    sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM", "STTM"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA.16816" not in sass
+
+
+def test_compute_entry_points_fail_loudly_without_cuda():
+    from rollingdepth_b200 import ops, _lib as L
+    from rollingdepth_b200.depth_aligner import DepthAligner
+    q = torch.zeros(1, 8, 1, 64, dtype=torch.float16)
+    with pytest.raises(L.RdError):
+        ops.xattn_fwd(q, q, q)
+    with pytest.raises(L.RdError):
+        DepthAligner(device=torch.device("cpu")).run([torch.zeros(2, 3, 1, 24, 24)], [1])
+    if not torch.cuda.is_available():
+        assert L.lib().rd_device_arch() < 0
+        assert b"CUDA" in L.lib().rd_last_error()
+
+
+def test_problem_init_and_argument_checks():
+    import ctypes as C
+    from rollingdepth_b200 import _lib as L
+    pb = L.CoalignProblem()
+    pb.G, pb.w, pb.N, pb.H, pb.W, pb.border, pb.factor = 2, 3, 150, 432, 768, 2, 10
+    pb.d[0], pb.d[1] = 1, 25
+    assert L.lib().rd_coalign_problem_init(C.byref(pb)) == 0
+    assert (pb.n[0], pb.n[1], pb.n_total) == (148, 100, 248)
+    assert (pb.Hs, pb.Ws, pb.P, pb.P_pad) == (43, 77, 3311, 3312)
+    pb.border = 0      # the reference's [border:-border] slice is empty for 0
+    assert L.lib().rd_coalign_problem_init(C.byref(pb)) == -1
+    assert b"border" in L.lib().rd_last_error()
+    pb.border, pb.d[1] = 2, 80
+    assert L.lib().rd_coalign_problem_init(C.byref(pb)) == -1   # dilation too large for the clip
+
+
+def test_block_partition_is_balanced_and_contiguous():
+    from rollingdepth_b200.sharding import Shard
+    for n in (0, 1, 7, 100, 148, 378):
+        for world in (1, 2, 3, 4, 8):
+            blocks = [Shard.block_of(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["RD_ROOT"])
+from rollingdepth_b200.sharding import Shard
+from oracle import schedule as osch
+dist.init_process_group("gloo")
+sh = Shard.from_dist()
+# (1) uneven block all-gather reproduces the full tensor in rank order
+total = 7
+full = torch.arange(total * 3, dtype=torch.float32).reshape(total, 3)
+lo, hi = sh.block(total)
+got = sh.all_gather_blocks(full[lo:hi].clone(), total)
+assert torch.equal(got, full), (got, full)
+buf = torch.zeros_like(full); buf[lo:hi] = full[lo:hi]
+assert torch.equal(sh.all_gather_blocks(buf, total), full)
+# (2) snippet-sharded "denoise": every rank processes its block of snippets, results are identical to 1 rank
+N, n, d = 30, 3, 4
+idx = osch.get_snippet_indice(0, 1, N, n, d, d, 1)
+frames = torch.arange(N, dtype=torch.float32)
+def work(ix): return torch.stack([frames[i].sum() * 2 + 1 for i in map(torch.tensor, ix)])
+lo, hi = sh.block(len(idx))
+mine = work(idx[lo:hi])
+allr = sh.all_gather_blocks(mine, len(idx))
+assert torch.equal(allr, work(idx))
+# (3) per-frame partial sums of the merge: all-reduce(sum) equals the single-rank sums
+acc = torch.zeros(N); cnt = torch.zeros(N)
+for k in range(lo, hi):
+    for j, f in enumerate(idx[k]):
+        acc[f] += float(k + j); cnt[f] += 1
+sh.all_reduce_(acc); sh.all_reduce_(cnt)
+ref_a = torch.zeros(N); ref_c = torch.zeros(N)
+for k in range(len(idx)):
+    for j, f in enumerate(idx[k]):
+        ref_a[f] += float(k + j); ref_c[f] += 1
+assert torch.equal(acc, ref_a) and torch.equal(cnt, ref_c)
+mn = torch.tensor([float(sh.rank + 3)]); sh.all_reduce_(mn, "min"); assert float(mn) == 3.0
+dist.destroy_process_group()
+print("rank", sh.rank, "ok")
+'''
+
+
+def test_sharding_collectives_world2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, RD_ROOT=ROOT, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                       capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2

@@ -215,8 +215,9 @@ def test_ddim_step_vs_reference(golden_dir, tag, ptype):
                 y = sch.step(v, ts[pos], x)
                 assert torch.equal(y, orc.step(v, ts[pos], x)), (tag, n, dn, pos)
                 ref = torch.from_numpy(g[f"{tag}_n{n}_{dn}_p{pos}_y"]).to(dev)
-                tol = 1e-6 if dt == torch.float32 else 2.0 ** -8
-                assert float((y.float() - ref.float()).abs().max()) <= tol
+                # CPU fixture: a few fp16 ulps (the CPU path rounds the schedule scalars to fp16 first)
+                rel = 2e-6 if dt == torch.float32 else 4 * 2.0 ** -11
+                assert float(((y.float() - ref.float()).abs() / ref.float().abs().clamp_min(1.0)).max()) <= rel
     sch = DDIMSchedule(**kw)
     sch.set_timesteps(20)
     for dn in ("f32", "f16"):

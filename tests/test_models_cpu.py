@@ -1,0 +1,99 @@
+"""CPU checks of the host-side model code and of the oracle pipeline against reference fixtures
+(tests/golden/models_pipeline.npz, sd2_state_keys.json -- produced by oracle/gen_golden_pipeline.py from the
+reference's vendored diffusers + rollingdepth_pipeline.py)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import model_utils as mu
+from oracle import pipeline as opipe
+from rollingdepth_b200.sd2.unet import UNet2DConditionModel
+from rollingdepth_b200.sd2.vae import AutoencoderKL
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "models_pipeline.npz"))
+
+
+def _strip(cfg):
+    return {k: v for k, v in cfg.items() if k not in ("down_block_types", "up_block_types") or "Encoder" not in str(v)}
+
+
+def test_state_dict_keys_match_diffusers(golden_dir):
+    """A diffusers SD2 checkpoint (e.g. prs-eth/rollingdepth-v1-0) must load with strict=True."""
+    ref = json.load(open(os.path.join(golden_dir, "sd2_state_keys.json")))
+    with torch.device("meta"):
+        unet = UNet2DConditionModel(**mu.SD2_UNET)
+        vae = AutoencoderKL(**{k: v for k, v in mu.SD_VAE.items() if not k.endswith("block_types")})
+    ours_u = {k: list(v.shape) for k, v in unet.state_dict().items()}
+    ours_v = {k: list(v.shape) for k, v in vae.state_dict().items()}
+    assert ours_u == ref["unet"]
+    assert ours_v == ref["vae"]
+    assert 860e6 < sum(int(np.prod(s)) for s in ours_u.values()) < 870e6   # 866 M parameters
+
+
+def _tiny():
+    unet = mu.deterministic_init_(UNet2DConditionModel(**mu.TINY_UNET).eval(), seed=1)
+    vae = mu.deterministic_init_(AutoencoderKL(**{k: v for k, v in mu.TINY_VAE.items() if not k.endswith("block_types")}).eval(), seed=2)
+    return unet, vae
+
+
+@pytest.mark.parametrize("tag", ["even", "odd", "n4"])
+def test_unet_forward_matches_reference(gold, tag):
+    unet, _ = _tiny()
+    x = torch.from_numpy(gold[f"unet_{tag}_x"])
+    ctx = torch.from_numpy(gold[f"unet_{tag}_ctx"])
+    n = x.shape[0]
+    with torch.no_grad():
+        y = unet(x, torch.full((n,), 999), encoder_hidden_states=ctx, num_view=n).sample
+        y_pf = unet(x, torch.full((n,), 999), encoder_hidden_states=ctx, num_view=None).sample
+    assert float((y - torch.from_numpy(gold[f"unet_{tag}_y"])).abs().max()) < 2e-5
+    assert float((y_pf - torch.from_numpy(gold[f"unet_{tag}_y_perframe"])).abs().max()) < 2e-5
+    assert float((y - y_pf).abs().max()) > 1e-4   # cross-frame attention must matter
+
+
+def test_vae_matches_reference(gold):
+    _, vae = _tiny()
+    img = torch.from_numpy(gold["vae_img"])
+    with torch.no_grad():
+        mom = vae.quant_conv(vae.encoder(img))
+        dec = vae.decoder(vae.post_quant_conv(mom[:, :4]))
+    assert float((mom - torch.from_numpy(gold["vae_moments"])).abs().max()) < 2e-5
+    assert float((dec - torch.from_numpy(gold["vae_dec"])).abs().max()) < 2e-5
+
+
+def test_attention_refuses_processor_without_num_view():
+    from rollingdepth_b200.sd2.layers import Attention
+
+    class NoView:
+        def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None):
+            return hidden_states
+
+    a = Attention(64, None, 1, 64, processor=NoView())
+    with pytest.raises(TypeError):
+        a(torch.zeros(3, 4, 64), num_view=3)
+
+
+@pytest.mark.parametrize("tag,kw", [("norefine", dict(dilations=[1, 3], refine_step=0)),
+                                    ("refine", dict(dilations=[1, 2, 3], refine_step=2))])
+def test_oracle_pipeline_matches_reference(gold, tag, kw):
+    """The oracle's restatement of RollingDepthPipeline.forward against the reference's own output
+    (CPU fp32, tiny SD2-architecture models, 10 frames)."""
+    unet, vae = _tiny()
+    frames = torch.from_numpy(gold["pipe_frames"])
+    res = opipe.forward(unet, vae, mu.DDIM_CFG, torch.from_numpy(gold["pipe_text"]), frames, cap_dilation=True,
+                        coalign_kwargs=dict(num_iterations=30), refine_start_dilation=3,
+                        generator=torch.Generator().manual_seed(0), **kw)
+    for i, s in enumerate(res.snippet_ls):
+        assert float((s - torch.from_numpy(gold[f"pipe_{tag}_snip{i}"])).abs().max()) < 5e-5
+    co = torch.from_numpy(gold[f"pipe_{tag}_coaligned"])
+    dp = torch.from_numpy(gold[f"pipe_{tag}_depth_pred"])
+    assert float((res.depth_coaligned.squeeze(0) - co).abs().max()) < 2e-3
+    assert float((res.depth_pred - dp).abs().max()) < 5e-3
+    d0, d1 = (res.depth_pred + 1) / 2, (dp + 1) / 2
+    absrel = float(((d0 - d1).abs() / d1.clamp_min(1e-3)).mean())
+    assert absrel <= 1e-3, absrel
