@@ -192,9 +192,9 @@ def run_ours(args):
     hbm, tf_burst, tf_sust, peak_src = peaks()
 
     unet, vae = build_models(dev, dtype)
-    if args.channels_last:
-        unet.to(memory_format=torch.channels_last); vae.to(memory_format=torch.channels_last)
-    pipe = RollingDepthPipeline(unet, vae, DDIMSchedule(), snippet_batch=args.snippet_batch)
+    torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
+    pipe = RollingDepthPipeline(unet, vae, DDIMSchedule(), snippet_batch=args.snippet_batch,
+                                channels_last=bool(args.channels_last), fused_norm=bool(args.fused_norm))
     if world > 1:
         pipe.enable_sharding()
     pipe.empty_text_embed = torch.randn(1, 2, 1024, generator=torch.Generator().manual_seed(1)).to(dev, dtype)
@@ -278,7 +278,8 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": str(dtype).split(".")[-1].replace("float", "f").replace("bf", "bf"), "data": "synthetic",
             "config": {**workload_config(args.preset, world), "snippet_batch": args.snippet_batch,
-                       "max_vae_bs": args.max_vae_bs, "channels_last": bool(args.channels_last)},
+                       "max_vae_bs": args.max_vae_bs, "channels_last": bool(args.channels_last),
+                       "fused_norm": bool(args.fused_norm), "cudnn_benchmark": bool(args.cudnn_benchmark)},
             "clocks": sampler.summary(),
             "e2e": {"value": n * k2 / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": k2},
@@ -300,6 +301,8 @@ if __name__ == "__main__":
     ap.add_argument("--snippet-batch", type=int, default=8)
     ap.add_argument("--max-vae-bs", type=int, default=12)
     ap.add_argument("--channels-last", type=int, default=1)
+    ap.add_argument("--fused-norm", type=int, default=1)
+    ap.add_argument("--cudnn-benchmark", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     if a.impl == "reference":

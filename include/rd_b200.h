@@ -186,6 +186,19 @@ int rd_merge(const void* const* host_snip_ptrs, const rd_coalign_problem* p, con
  * (rollingdepth_pipeline.py:316-318); minmax = {mn, mx} from rd_merge. */
 int rd_renorm(void* depth, int64_t n, const float* dev_minmax, rd_dtype dtype, void* stream);
 
+/* ------------------------------------------------------------------ (4) fused GroupNorm (+ SiLU), channels-last
+ * Replaces the GroupNorm -> SiLU pairs in front of every convolution of the UNet / VAE resnets
+ * (diffusers/src/diffusers/models/resnet.py:320-376: norm1/nonlinearity, norm2/nonlinearity), the
+ * conv_norm_out/conv_act pairs (autoencoders/vae.py:160-165, 325-333; unets/unet_2d_condition.py:1312-1315)
+ * and the act-free norms of Transformer2DModel (:418) and the VAE mid-block attention.
+ * x, y: [N, HW, C] with C contiguous (= NCHW tensors in torch.channels_last memory format); gamma/beta: [C]
+ * in the activation dtype (NULL = 1 / 0).  y = act(round(groupnorm(x))); statistics in fp32/fp64.
+ * act: 0 = identity, 1 = SiLU.  workspace >= rd_groupnorm_workspace_bytes(N, G). */
+int64_t rd_groupnorm_workspace_bytes(int N, int G);
+int rd_groupnorm_nhwc(const void* x, void* y, const void* gamma, const void* beta,
+                      int N, int HW, int C, int G, float eps, int act, rd_dtype dtype,
+                      void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,7 +56,7 @@ class B200XFrameAttnProcessor:
         input_ndim = hidden_states.ndim
         if input_ndim == 4:
             batch_size, channel, height, width = hidden_states.shape
-            hidden_states = hidden_states.view(batch_size, channel, height * width).transpose(1, 2)
+            hidden_states = hidden_states.reshape(batch_size, channel, height * width).transpose(1, 2)
 
         if num_view is not None:                                     # "(b n) hw c -> b (n hw) c"
             bn, hw, c = hidden_states.shape
@@ -65,7 +65,11 @@ class B200XFrameAttnProcessor:
             hidden_states = hidden_states.reshape(bn // num_view, num_view * hw, c)
 
         if getattr(attn, "group_norm", None) is not None:
-            hidden_states = attn.group_norm(hidden_states.transpose(1, 2)).transpose(1, 2)
+            gn = attn.group_norm
+            if hasattr(gn, "forward_nlc"):      # our GroupNormAct: NHWC kernel, no transposes
+                hidden_states = gn.forward_nlc(hidden_states)
+            else:
+                hidden_states = gn(hidden_states.transpose(1, 2)).transpose(1, 2)
 
         query = attn.to_q(hidden_states)
 

@@ -89,3 +89,34 @@ def renorm_(depth: torch.Tensor, minmax: torch.Tensor) -> torch.Tensor:
     L.check(code, "rd_renorm")
     L.count_launches(1)
     return depth
+
+
+def group_norm_nhwc(x: torch.Tensor, num_groups: int, weight: Optional[torch.Tensor], bias: Optional[torch.Tensor],
+                    eps: float, silu: bool) -> torch.Tensor:
+    """GroupNorm (+SiLU) on a channels-last activation: x is [N, C, H, W] in torch.channels_last memory format
+    or [N, L, C] contiguous.  Returns a tensor with the same shape / memory format."""
+    L.require_cuda(x)
+    if x.dim() == 4:
+        N, Cc, H, W = x.shape
+        if not x.is_contiguous(memory_format=torch.channels_last):
+            raise L.RdError("group_norm_nhwc needs a channels_last tensor")
+        HW = H * W
+        y = torch.empty_like(x, memory_format=torch.channels_last)
+    elif x.dim() == 3:
+        N, HW, Cc = x.shape
+        if not x.is_contiguous():
+            raise L.RdError("group_norm_nhwc needs a contiguous [N, L, C] tensor")
+        y = torch.empty_like(x)
+    else:
+        raise L.RdError("group_norm_nhwc expects a 3-D or 4-D tensor")
+    lib = L.lib()
+    ws_bytes = lib.rd_groupnorm_workspace_bytes(N, num_groups)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    g = weight.to(x.dtype) if weight is not None else None
+    b = bias.to(x.dtype) if bias is not None else None
+    code = lib.rd_groupnorm_nhwc(L.ptr(x), L.ptr(y), L.ptr(g) if g is not None else None, L.ptr(b) if b is not None else None,
+                                 N, HW, Cc, int(num_groups), float(eps), 1 if silu else 0, L.dtype_code(x.dtype),
+                                 L.ptr(ws), ws_bytes, L.stream_ptr(x.device))
+    L.check(code, "rd_groupnorm_nhwc")
+    L.count_launches(2)
+    return y

@@ -47,7 +47,7 @@ class RollingDepthPipeline:
     N_CHANNEL_PER_LATENT = 4
 
     def __init__(self, unet, vae, scheduler, text_encoder=None, tokenizer=None, snippet_batch: int = 8,
-                 install_processor: bool = True):
+                 install_processor: bool = True, channels_last: bool = True, fused_norm: bool = True):
         self.unet = unet
         self.vae = vae
         self.scheduler = DDIMSchedule.from_scheduler(scheduler)
@@ -57,6 +57,8 @@ class RollingDepthPipeline:
         self.snippet_batch = int(snippet_batch)
         self.shard = Shard()            # single rank unless torch.distributed is initialised (see enable_sharding)
         self.timings: Dict[str, float] = {}
+        self.channels_last, self.fused_norm = bool(channels_last), bool(fused_norm)
+        self._tuned_for = None
         if install_processor:
             self.unet.set_attn_processor(B200XFrameAttnProcessor())
         logging.debug(f"Pipeline initialized: {type(self)}")
@@ -75,6 +77,21 @@ class RollingDepthPipeline:
     @property
     def dtype(self) -> torch.dtype:
         return next(self.unet.parameters()).dtype
+
+    def _tune_modules(self) -> None:
+        """NHWC weights for cuDNN's Blackwell convolutions and the fused NHWC GroupNorm(+SiLU) kernel on every
+        norm of our SD2 modules (diffusers modules are left as they are).  Idempotent; redone if the device changes."""
+        key = (self.device, self.dtype)
+        if self._tuned_for == key:
+            return
+        from .sd2.layers import GroupNormAct
+        for m in (self.unet, self.vae):
+            if self.channels_last:
+                m.to(memory_format=torch.channels_last)
+            for sub in m.modules():
+                if isinstance(sub, GroupNormAct):
+                    sub.fused = self.fused_norm
+        self._tuned_for = key
 
     def enable_sharding(self, group=None) -> "RollingDepthPipeline":
         """Shard snippets over the ranks of `group` (default: the world group)."""
@@ -189,6 +206,7 @@ class RollingDepthPipeline:
             raise L.RdError("RollingDepthPipeline (B200) must be on a CUDA device; there is no CPU fallback")
         if input_frames.shape[0] != 1:
             raise NotImplementedError("Layered inference is only implemented for B=1")
+        self._tune_modules()
 
         # ----------------- Initial prediction -----------------
         input_frames = input_frames.to(self.dtype).to(device, non_blocking=True)      # :263

@@ -48,6 +48,63 @@ class TimestepEmbedding(nn.Module):
         return self.linear_2(self.act(self.linear_1(sample)))
 
 
+# --------------------------------------------------------------------------- GroupNorm (+SiLU)
+class GroupNormAct(nn.GroupNorm):
+    """`nn.GroupNorm` (same parameters / state-dict keys) with an optional trailing SiLU.
+
+    With `fused = True` (set by the B200 pipeline) CUDA channels-last inputs go to the hand-written NHWC
+    kernel pair (C ABI rd_groupnorm_nhwc): statistics + normalise + SiLU in 2 reads and 1 write, no layout
+    round trips.  Otherwise it is exactly F.group_norm followed by F.silu -- the fp32 reference of that kernel.
+    """
+
+    def __init__(self, num_groups: int, num_channels: int, eps: float = 1e-5, act: bool = False):
+        super().__init__(num_groups, num_channels, eps=eps, affine=True)
+        self.act = act
+        self.fused = False
+
+    def _fusable(self, x: torch.Tensor) -> bool:
+        return (self.fused and x.is_cuda and x.dtype in (torch.float16, torch.bfloat16, torch.float32)
+                and self.num_channels % (16 // x.element_size()) == 0 and self.num_channels // (16 // x.element_size()) <= 512)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dim() == 4 and self._fusable(x) and x.is_contiguous(memory_format=torch.channels_last):
+            from .. import ops
+            return ops.group_norm_nhwc(x, self.num_groups, self.weight, self.bias, self.eps, self.act)
+        y = F.group_norm(x, self.num_groups, self.weight, self.bias, self.eps)
+        return F.silu(y) if self.act else y
+
+    def forward_nlc(self, x: torch.Tensor) -> torch.Tensor:
+        """[N, L, C] in, [N, L, C] out (the layout attention processors hold)."""
+        if self._fusable(x) and x.is_contiguous():
+            from .. import ops
+            return ops.group_norm_nhwc(x, self.num_groups, self.weight, self.bias, self.eps, self.act)
+        y = F.group_norm(x.transpose(1, 2), self.num_groups, self.weight, self.bias, self.eps).transpose(1, 2)
+        return F.silu(y) if self.act else y
+
+
+def _to_nlc(x4: torch.Tensor) -> torch.Tensor:
+    """[B, C, H, W] -> [B, H*W, C] without a copy for either memory format where possible."""
+    b, c, h, w = x4.shape
+    if x4.is_contiguous(memory_format=torch.channels_last) and not x4.is_contiguous():
+        return x4.permute(0, 2, 3, 1).reshape(b, h * w, c)
+    return x4.reshape(b, c, h * w).transpose(1, 2)
+
+
+def _from_nlc(x3: torch.Tensor, like: torch.Tensor) -> torch.Tensor:
+    b, c, h, w = like.shape
+    if like.is_contiguous(memory_format=torch.channels_last) and not like.is_contiguous():
+        return x3.reshape(b, h, w, c).permute(0, 3, 1, 2)
+    return x3.transpose(-1, -2).reshape(b, c, h, w)
+
+
+def group_norm_nlc(attn, hidden_states: torch.Tensor) -> torch.Tensor:
+    """attn.group_norm on a [B, L, C] tensor (attention_processor.py:2223-2224)."""
+    gn = attn.group_norm
+    if hasattr(gn, "forward_nlc"):
+        return gn.forward_nlc(hidden_states)
+    return gn(hidden_states.transpose(1, 2)).transpose(1, 2)
+
+
 # --------------------------------------------------------------------------- attention (plug-in surface)
 class TorchSDPAProcessor:
     """Library attention (torch SDPA) with the reference's `num_view` semantics; used for the VAE
@@ -58,13 +115,12 @@ class TorchSDPAProcessor:
         residual = hidden_states
         input_ndim = hidden_states.ndim
         if input_ndim == 4:
-            b, c, h, w = hidden_states.shape
-            hidden_states = hidden_states.view(b, c, h * w).transpose(1, 2)
+            hidden_states = _to_nlc(hidden_states)
         if num_view is not None:
             bn, hw, c_ = hidden_states.shape
             hidden_states = hidden_states.reshape(bn // num_view, num_view * hw, c_)
         if attn.group_norm is not None:
-            hidden_states = attn.group_norm(hidden_states.transpose(1, 2)).transpose(1, 2)
+            hidden_states = group_norm_nlc(attn, hidden_states)
         query = attn.to_q(hidden_states)
         ctx = hidden_states if encoder_hidden_states is None else encoder_hidden_states
         if ctx.shape[0] != hidden_states.shape[0]:
@@ -82,7 +138,7 @@ class TorchSDPAProcessor:
             b_, s_, c_ = o.shape
             o = o.reshape(b_ * num_view, s_ // num_view, c_)
         if input_ndim == 4:
-            o = o.transpose(-1, -2).reshape(b, c, h, w)
+            o = _from_nlc(o, residual)
         if attn.residual_connection:
             o = o + residual
         return o / attn.rescale_output_factor
@@ -103,7 +159,7 @@ class Attention(nn.Module):
         self.scale = dim_head ** -0.5
         self.residual_connection = residual_connection
         self.rescale_output_factor = rescale_output_factor
-        self.group_norm = nn.GroupNorm(norm_num_groups, query_dim, eps=eps, affine=True) if norm_num_groups else None
+        self.group_norm = GroupNormAct(norm_num_groups, query_dim, eps=eps) if norm_num_groups else None
         self.spatial_norm = None
         self.norm_q = self.norm_k = None
         self.norm_cross = None
@@ -181,7 +237,7 @@ class Transformer2DModel(nn.Module):
         super().__init__()
         inner = heads * dim_head
         self.use_linear_projection = use_linear_projection
-        self.norm = nn.GroupNorm(norm_num_groups, in_channels, eps=1e-6, affine=True)
+        self.norm = GroupNormAct(norm_num_groups, in_channels, eps=1e-6)
         self.proj_in = nn.Linear(in_channels, inner) if use_linear_projection else nn.Conv2d(in_channels, inner, 1)
         self.transformer_blocks = nn.ModuleList(
             [BasicTransformerBlock(inner, heads, dim_head, cross_attention_dim) for _ in range(num_layers)])
@@ -201,7 +257,9 @@ class Transformer2DModel(nn.Module):
             x = blk(x, encoder_hidden_states=encoder_hidden_states, num_view=num_view)
         if self.use_linear_projection:
             x = self.proj_out(x)
-            x = x.reshape(b, h, w, -1).permute(0, 3, 1, 2).contiguous()
+            x = x.reshape(b, h, w, -1).permute(0, 3, 1, 2)       # a channels-last view, no copy
+            if not residual.is_contiguous(memory_format=torch.channels_last):
+                x = x.contiguous()
         else:
             x = x.reshape(b, h, w, -1).permute(0, 3, 1, 2).contiguous()
             x = self.proj_out(x)
@@ -215,10 +273,10 @@ class ResnetBlock2D(nn.Module):
     def __init__(self, in_channels: int, out_channels: int, temb_channels: Optional[int], groups: int = 32,
                  eps: float = 1e-5, output_scale_factor: float = 1.0):
         super().__init__()
-        self.norm1 = nn.GroupNorm(groups, in_channels, eps=eps, affine=True)
+        self.norm1 = GroupNormAct(groups, in_channels, eps=eps, act=True)      # GroupNorm -> SiLU (:338-339)
         self.conv1 = nn.Conv2d(in_channels, out_channels, 3, padding=1)
         self.time_emb_proj = nn.Linear(temb_channels, out_channels) if temb_channels is not None else None
-        self.norm2 = nn.GroupNorm(groups, out_channels, eps=eps, affine=True)
+        self.norm2 = GroupNormAct(groups, out_channels, eps=eps, act=True)
         self.dropout = nn.Dropout(0.0)
         self.conv2 = nn.Conv2d(out_channels, out_channels, 3, padding=1)
         self.nonlinearity = nn.SiLU()
@@ -226,10 +284,10 @@ class ResnetBlock2D(nn.Module):
         self.output_scale_factor = output_scale_factor
 
     def forward(self, x, temb=None):
-        h = self.conv1(self.nonlinearity(self.norm1(x)))
+        h = self.conv1(self.norm1(x))
         if self.time_emb_proj is not None and temb is not None:
             h = h + self.time_emb_proj(self.nonlinearity(temb))[:, :, None, None]
-        h = self.conv2(self.dropout(self.nonlinearity(self.norm2(h))))
+        h = self.conv2(self.dropout(self.norm2(h)))
         if self.conv_shortcut is not None:
             x = self.conv_shortcut(x)
         out = x + h

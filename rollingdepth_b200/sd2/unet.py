@@ -15,7 +15,7 @@ from typing import Dict, Optional, Sequence, Tuple, Union
 import torch
 import torch.nn as nn
 
-from .layers import (Attention, Downsample2D, ResnetBlock2D, TimestepEmbedding, Transformer2DModel, Upsample2D,
+from .layers import (Attention, Downsample2D, GroupNormAct, ResnetBlock2D, TimestepEmbedding, Transformer2DModel, Upsample2D,
                      timestep_embedding)
 
 SD2_UNET_CONFIG = dict(
@@ -137,7 +137,7 @@ class UNet2DConditionModel(nn.Module):
                 raise NotImplementedError(t)
             self.up_blocks.append(_UpBlock(cin, cout, cprev, temb, layers_per_block + 1, norm_num_groups, i != nb - 1, cfg))
 
-        self.conv_norm_out = nn.GroupNorm(norm_num_groups, block_out_channels[0], eps=1e-5)
+        self.conv_norm_out = GroupNormAct(norm_num_groups, block_out_channels[0], eps=1e-5, act=True)
         self.conv_act = nn.SiLU()
         self.conv_out = nn.Conv2d(block_out_channels[0], out_channels, 3, padding=1)
 
@@ -192,7 +192,7 @@ class UNet2DConditionModel(nn.Module):
             # the total stride (unet_2d_condition.py:1283-1287); for exact multiples this equals scale_factor=2
             size = skips[-1].shape[-2:] if (blk.upsamplers is not None and len(skips) > 0) else None
             x = blk(x, take, emb, encoder_hidden_states, num_view, size)
-        x = self.conv_out(self.conv_act(self.conv_norm_out(x)))
+        x = self.conv_out(self.conv_norm_out(x))        # conv_norm_out carries the SiLU (conv_act)
         if not return_dict:
             return (x,)
         return SimpleNamespace(sample=x)

@@ -15,7 +15,7 @@ from typing import Sequence
 import torch
 import torch.nn as nn
 
-from .layers import Attention, Downsample2D, ResnetBlock2D, Upsample2D
+from .layers import Attention, Downsample2D, GroupNormAct, ResnetBlock2D, Upsample2D
 
 SD_VAE_CONFIG = dict(in_channels=3, out_channels=3, latent_channels=4, block_out_channels=(128, 256, 512, 512),
                      layers_per_block=2, norm_num_groups=32)
@@ -73,7 +73,7 @@ class Encoder(nn.Module):
             cin, cout = cout, c
             self.down_blocks.append(_EncBlock(cin, cout, layers_per_block, groups, i != len(block_out_channels) - 1))
         self.mid_block = _VaeMid(block_out_channels[-1], groups, block_out_channels[-1])
-        self.conv_norm_out = nn.GroupNorm(groups, block_out_channels[-1], eps=1e-6)
+        self.conv_norm_out = GroupNormAct(groups, block_out_channels[-1], eps=1e-6, act=True)
         self.conv_act = nn.SiLU()
         self.conv_out = nn.Conv2d(block_out_channels[-1], 2 * out_channels if double_z else out_channels, 3, padding=1)
 
@@ -82,7 +82,7 @@ class Encoder(nn.Module):
         for b in self.down_blocks:
             x = b(x)
         x = self.mid_block(x)
-        return self.conv_out(self.conv_act(self.conv_norm_out(x)))
+        return self.conv_out(self.conv_norm_out(x))      # conv_norm_out carries the SiLU (conv_act)
 
 
 class Decoder(nn.Module):
@@ -96,7 +96,7 @@ class Decoder(nn.Module):
         for i, c in enumerate(rev):
             cin, cout = cout, c
             self.up_blocks.append(_DecBlock(cin, cout, layers_per_block + 1, groups, i != len(rev) - 1))
-        self.conv_norm_out = nn.GroupNorm(groups, rev[-1], eps=1e-6)
+        self.conv_norm_out = GroupNormAct(groups, rev[-1], eps=1e-6, act=True)
         self.conv_act = nn.SiLU()
         self.conv_out = nn.Conv2d(rev[-1], out_channels, 3, padding=1)
 
@@ -105,7 +105,7 @@ class Decoder(nn.Module):
         x = self.mid_block(x)
         for b in self.up_blocks:
             x = b(x)
-        return self.conv_out(self.conv_act(self.conv_norm_out(x)))
+        return self.conv_out(self.conv_norm_out(x))      # conv_norm_out carries the SiLU (conv_act)
 
 
 class AutoencoderKL(nn.Module):

@@ -45,6 +45,9 @@ def test_pipeline_fp32_matches_reference_fixture(golden_dir, tag, dil, refine, s
     from rollingdepth_b200.pipeline import RollingDepthPipeline
     from rollingdepth_b200.scheduler import DDIMSchedule
     dev = _dev()
+    # the fixture is a CPU fp32 run: keep cuDNN / cuBLAS in true fp32 (torch allows TF32 convolutions by default)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     g = np.load(os.path.join(golden_dir, "models_pipeline.npz"))
     unet, vae = _tiny(dev, torch.float32)
     pipe = RollingDepthPipeline(unet, vae, DDIMSchedule(**mu.DDIM_CFG), snippet_batch=snippet_batch)
