@@ -193,11 +193,24 @@ int rd_renorm(void* depth, int64_t n, const float* dev_minmax, rd_dtype dtype, v
  * and the act-free norms of Transformer2DModel (:418) and the VAE mid-block attention.
  * x, y: [N, HW, C] with C contiguous (= NCHW tensors in torch.channels_last memory format); gamma/beta: [C]
  * in the activation dtype (NULL = 1 / 0).  y = act(round(groupnorm(x))); statistics in fp32/fp64.
- * act: 0 = identity, 1 = SiLU.  workspace >= rd_groupnorm_workspace_bytes(N, G). */
+ * act: 0 = identity, 1 = SiLU.  workspace >= rd_groupnorm_workspace_bytes(N, G).
+ * pre_add: optional [N, C] vector (activation dtype) added to x first: y = act(GN(round(x + pre_add[n, c]))) --
+ * the bias of the preceding (bias-free) convolution plus the projected time embedding (resnet.py:341-352). */
 int64_t rd_groupnorm_workspace_bytes(int N, int G);
-int rd_groupnorm_nhwc(const void* x, void* y, const void* gamma, const void* beta,
+int rd_groupnorm_nhwc(const void* x, void* y, const void* gamma, const void* beta, const void* pre_add,
                       int N, int HW, int C, int G, float eps, int act, rd_dtype dtype,
                       void* workspace, int64_t workspace_bytes, void* stream);
+
+/* y = x + bias[c] + vec[n, c] + residual in one vectorised pass over [N, HW, C] (any of bias / vec / residual may be
+ * NULL; y may alias x): conv bias, time-embedding add and skip connection (resnet.py:341-376) without separate
+ * element-wise launches.  Arithmetic in fp32, one rounding. */
+int rd_bias_residual_nhwc(const void* x, const void* bias, const void* vec, const void* residual, void* y,
+                          int N, int HW, int C, rd_dtype dtype, void* stream);
+
+/* Nearest-neighbour resize of an NHWC activation, index rule of torch F.interpolate(mode="nearest")
+ * (upsampling.py Upsample2D.forward). */
+int rd_upsample_nearest_nhwc(const void* x, void* y, int N, int Hi, int Wi, int Ho, int Wo, int C,
+                             rd_dtype dtype, void* stream);
 
 #ifdef __cplusplus
 }

@@ -23,9 +23,11 @@ struct GnParams {
     void* y;
     const void* gamma;
     const void* beta;
+    const void* pre;      // optional [N][C] vector added to x before the statistics (conv bias + time embedding)
     double* partial;      // [N][chunks][G][2]  (sum x, sum x^2)
     int N, HW, C, G, cpg;  // cpg = channels per group
-    int CV;                // C / 8 (16-bit types) or C / 4 (fp32): 16-byte vectors per pixel
+    int Cs;                // channels per CTA slice (blockIdx.z selects the slice); Cs % cpg == 0
+    int CV;                // Cs / 8 (16-bit types) or Cs / 4 (fp32): 16-byte vectors per pixel and slice
     int R;                 // pixel rows processed concurrently by one CTA
     int chunks, rows_per_chunk;
     float eps;
@@ -49,45 +51,49 @@ __device__ __forceinline__ void gn_unpack(const uint4& u, float* f) {
 template <typename T>
 __global__ void __launch_bounds__(kGnMaxThreads) gn_stats_kernel(const GnParams p) {
     constexpr int VN = GnVec<T>::N;
-    extern __shared__ double sh_d[];                  // [2][C] channel sums (double)
+    extern __shared__ double sh_d[];                  // [2][Cs] channel sums (double)
     double* ch_sum = sh_d;
-    double* ch_sq = sh_d + p.C;
+    double* ch_sq = sh_d + p.Cs;
     const int n = blockIdx.y, chunk = blockIdx.x;
+    const int c_off = blockIdx.z * p.Cs;
     const int cv = threadIdx.x % p.CV, r = threadIdx.x / p.CV;
     const bool active = r < p.R;
-    const T* xs = reinterpret_cast<const T*>(p.x) + (size_t)n * p.HW * p.C;
+    const T* xs = reinterpret_cast<const T*>(p.x) + (size_t)n * p.HW * p.C + c_off;
     const int row0 = chunk * p.rows_per_chunk;
     const int row1 = min(p.HW, row0 + p.rows_per_chunk);
 
-    for (int c = threadIdx.x; c < 2 * p.C; c += blockDim.x) sh_d[c] = 0.0;
+    for (int c = threadIdx.x; c < 2 * p.Cs; c += blockDim.x) sh_d[c] = 0.0;
     __syncthreads();
 
-    float shift[VN], s1[VN], s2[VN];
+    float shift[VN], s1[VN], s2[VN], pre[VN];
     if (active) {
+#pragma unroll
+        for (int i = 0; i < VN; ++i) pre[i] = 0.f;
+        if (p.pre) gn_unpack<T>(*reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.pre) + (size_t)n * p.C + c_off + cv * VN), pre);
         gn_unpack<T>(*reinterpret_cast<const uint4*>(xs + (size_t)cv * VN), shift);   // pixel 0 of the sample
 #pragma unroll
-        for (int i = 0; i < VN; ++i) { s1[i] = 0.f; s2[i] = 0.f; }
+        for (int i = 0; i < VN; ++i) { shift[i] = Cvt<T>::round(shift[i] + pre[i]); s1[i] = 0.f; s2[i] = 0.f; }
         int row = row0 + r;
         // two independent 16-byte loads in flight per thread
         for (; row + p.R < row1; row += 2 * p.R) {
-            const uint4 a = ldg_stream16(xs + ((size_t)row * p.CV + cv) * VN);
-            const uint4 b = ldg_stream16(xs + ((size_t)(row + p.R) * p.CV + cv) * VN);
+            const uint4 a = ldg_stream16(xs + (size_t)row * p.C + cv * VN);
+            const uint4 b = ldg_stream16(xs + (size_t)(row + p.R) * p.C + cv * VN);
             float fa[VN], fb[VN];
             gn_unpack<T>(a, fa);
             gn_unpack<T>(b, fb);
 #pragma unroll
             for (int i = 0; i < VN; ++i) {
-                const float da = fa[i] - shift[i], db = fb[i] - shift[i];
+                const float da = Cvt<T>::round(fa[i] + pre[i]) - shift[i], db = Cvt<T>::round(fb[i] + pre[i]) - shift[i];
                 s1[i] += da + db;
                 s2[i] = fmaf(da, da, fmaf(db, db, s2[i]));
             }
         }
         for (; row < row1; row += p.R) {
             float fa[VN];
-            gn_unpack<T>(ldg_stream16(xs + ((size_t)row * p.CV + cv) * VN), fa);
+            gn_unpack<T>(ldg_stream16(xs + (size_t)row * p.C + cv * VN), fa);
 #pragma unroll
             for (int i = 0; i < VN; ++i) {
-                const float da = fa[i] - shift[i];
+                const float da = Cvt<T>::round(fa[i] + pre[i]) - shift[i];
                 s1[i] += da;
                 s2[i] = fmaf(da, da, s2[i]);
             }
@@ -106,10 +112,11 @@ __global__ void __launch_bounds__(kGnMaxThreads) gn_stats_kernel(const GnParams 
     // channels -> groups (fixed order => deterministic up to the shared-memory atomics above, which add
     // at most R <= 32 doubles per address; double addition of these magnitudes is order-insensitive to
     // ~1e-16 relative, far below the fp16/fp32 output rounding)
-    for (int g = threadIdx.x; g < p.G; g += blockDim.x) {
+    const int Gs = p.Cs / p.cpg, g0 = c_off / p.cpg;
+    for (int g = threadIdx.x; g < Gs; g += blockDim.x) {
         double a = 0.0, b = 0.0;
         for (int c = g * p.cpg; c < (g + 1) * p.cpg; ++c) { a += ch_sum[c]; b += ch_sq[c]; }
-        double* out = p.partial + (((size_t)n * p.chunks + chunk) * p.G + g) * 2;
+        double* out = p.partial + (((size_t)n * p.chunks + chunk) * p.G + g0 + g) * 2;
         out[0] = a;
         out[1] = b;
     }
@@ -119,14 +126,16 @@ __global__ void __launch_bounds__(kGnMaxThreads) gn_stats_kernel(const GnParams 
 template <typename T>
 __global__ void __launch_bounds__(kGnMaxThreads) gn_apply_kernel(const GnParams p) {
     constexpr int VN = GnVec<T>::N;
-    extern __shared__ float sh_f[];                   // [2][C] : a_c, b_c
+    extern __shared__ float sh_f[];                   // [2][Cs] : a_c, b_c
     __shared__ float g_mean[64], g_rstd[64];
     float* sa = sh_f;
-    float* sb = sh_f + p.C;
+    float* sb = sh_f + p.Cs;
     const int n = blockIdx.y, chunk = blockIdx.x;
-    for (int g = threadIdx.x; g < p.G; g += blockDim.x) {
+    const int c_off = blockIdx.z * p.Cs;
+    const int Gs = p.Cs / p.cpg, g0 = c_off / p.cpg;
+    for (int g = threadIdx.x; g < Gs; g += blockDim.x) {
         double a = 0.0, b = 0.0;
-        const double* part = p.partial + ((size_t)n * p.chunks * p.G + g) * 2;
+        const double* part = p.partial + ((size_t)n * p.chunks * p.G + g0 + g) * 2;
         for (int c = 0; c < p.chunks; ++c) { a += part[(size_t)c * p.G * 2]; b += part[(size_t)c * p.G * 2 + 1]; }
         const double cnt = (double)p.HW * (double)p.cpg;
         const double mean = a / cnt;
@@ -136,10 +145,10 @@ __global__ void __launch_bounds__(kGnMaxThreads) gn_apply_kernel(const GnParams 
         g_rstd[g] = rsqrtf((float)var + p.eps);
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < p.C; c += blockDim.x) {
+    for (int c = threadIdx.x; c < p.Cs; c += blockDim.x) {
         const int g = c / p.cpg;
-        const float gam = p.gamma ? Cvt<T>::to_f(reinterpret_cast<const T*>(p.gamma)[c]) : 1.f;
-        const float bet = p.beta ? Cvt<T>::to_f(reinterpret_cast<const T*>(p.beta)[c]) : 0.f;
+        const float gam = p.gamma ? Cvt<T>::to_f(reinterpret_cast<const T*>(p.gamma)[c_off + c]) : 1.f;
+        const float bet = p.beta ? Cvt<T>::to_f(reinterpret_cast<const T*>(p.beta)[c_off + c]) : 0.f;
         const float a = g_rstd[g] * gam;
         sa[c] = a;
         sb[c] = fmaf(-a, g_mean[g], bet);
@@ -148,21 +157,23 @@ __global__ void __launch_bounds__(kGnMaxThreads) gn_apply_kernel(const GnParams 
 
     const int cv = threadIdx.x % p.CV, r = threadIdx.x / p.CV;
     if (r >= p.R) return;
-    float a[VN], b[VN];
+    float a[VN], b[VN], pre[VN];
 #pragma unroll
-    for (int i = 0; i < VN; ++i) { a[i] = sa[cv * VN + i]; b[i] = sb[cv * VN + i]; }
-    const T* xs = reinterpret_cast<const T*>(p.x) + (size_t)n * p.HW * p.C;
-    T* ys = reinterpret_cast<T*>(p.y) + (size_t)n * p.HW * p.C;
+    for (int i = 0; i < VN; ++i) { a[i] = sa[cv * VN + i]; b[i] = sb[cv * VN + i]; pre[i] = 0.f; }
+    if (p.pre) gn_unpack<T>(*reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.pre) + (size_t)n * p.C + c_off + cv * VN), pre);
+    const T* xs = reinterpret_cast<const T*>(p.x) + (size_t)n * p.HW * p.C + c_off;
+    T* ys = reinterpret_cast<T*>(p.y) + (size_t)n * p.HW * p.C + c_off;
     const int row0 = chunk * p.rows_per_chunk;
     const int row1 = min(p.HW, row0 + p.rows_per_chunk);
     for (int row = row0 + r; row < row1; row += p.R) {
-        const size_t off = ((size_t)row * p.CV + cv) * VN;
+        const size_t off = (size_t)row * p.C + cv * VN;
         float f[VN];
         gn_unpack<T>(ldg_stream16(xs + off), f);
         alignas(16) T o[VN];
 #pragma unroll
         for (int i = 0; i < VN; ++i) {
-            float v = Cvt<T>::round(fmaf(f[i], a[i], b[i]));       // group_norm output, rounded to T like torch
+            const float xin = p.pre ? Cvt<T>::round(f[i] + pre[i]) : f[i];
+            float v = Cvt<T>::round(fmaf(xin, a[i], b[i]));        // group_norm output, rounded to T like torch
             if (p.act == 1) v = __fdividef(v, 1.f + __expf(-v));    // SiLU on the rounded value
             o[i] = Cvt<T>::from_f(v);
         }
@@ -170,9 +181,90 @@ __global__ void __launch_bounds__(kGnMaxThreads) gn_apply_kernel(const GnParams 
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// y = x + bias[c] + vec[n][c] + residual  (one vectorised pass; replaces the separate bias / time-embedding /
+// skip-connection element-wise kernels around the convolutions: resnet.py:341-376)
+struct AddParams {
+    const void* x; const void* bias; const void* vec; const void* res; void* y;
+    int N, HW, C, CV, R, chunks, rows_per_chunk;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kGnMaxThreads) bias_residual_kernel(const AddParams p) {
+    constexpr int VN = GnVec<T>::N;
+    const int n = blockIdx.y, chunk = blockIdx.x;
+    const int CVT = blockDim.x / p.R;                 // column vectors handled per pass
+    const int cv0 = threadIdx.x % CVT, r = threadIdx.x / CVT;
+    const int row0 = chunk * p.rows_per_chunk;
+    const int row1 = min(p.HW, row0 + p.rows_per_chunk);
+    for (int cv = cv0; cv < p.CV; cv += CVT) {
+        float add[VN];
+#pragma unroll
+        for (int i = 0; i < VN; ++i) add[i] = 0.f;
+        if (p.bias) {
+            float t[VN];
+            gn_unpack<T>(*reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.bias) + cv * VN), t);
+#pragma unroll
+            for (int i = 0; i < VN; ++i) add[i] += t[i];
+        }
+        if (p.vec) {
+            float t[VN];
+            gn_unpack<T>(*reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.vec) + (size_t)n * p.C + cv * VN), t);
+#pragma unroll
+            for (int i = 0; i < VN; ++i) add[i] += t[i];
+        }
+        const size_t base = (size_t)n * p.HW * p.C + cv * VN;
+        for (int row = row0 + r; row < row1; row += p.R) {
+            const size_t off = base + (size_t)row * p.C;
+            float f[VN];
+            gn_unpack<T>(ldg_stream16(reinterpret_cast<const T*>(p.x) + off), f);
+            if (p.res) {
+                float g[VN];
+                gn_unpack<T>(ldg_stream16(reinterpret_cast<const T*>(p.res) + off), g);
+#pragma unroll
+                for (int i = 0; i < VN; ++i) f[i] += g[i];
+            }
+            alignas(16) T o[VN];
+#pragma unroll
+            for (int i = 0; i < VN; ++i) o[i] = Cvt<T>::from_f(f[i] + add[i]);
+            *reinterpret_cast<uint4*>(reinterpret_cast<T*>(p.y) + off) = *reinterpret_cast<const uint4*>(o);
+        }
+    }
+}
+
+// nearest-neighbour resize of an NHWC activation (upsampling.py Upsample2D: F.interpolate(mode="nearest"))
+struct UpParams { const void* x; void* y; int N, Hi, Wi, Ho, Wo, CV; float sh, sw; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) upsample_nearest_nhwc_kernel(const UpParams p) {
+    const long long total = (long long)p.N * p.Ho * p.Wo * p.CV;
+    const uint4* xin = reinterpret_cast<const uint4*>(p.x);
+    uint4* yout = reinterpret_cast<uint4*>(p.y);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % p.CV);
+        long long t = i / p.CV;
+        const int wo = (int)(t % p.Wo); t /= p.Wo;
+        const int ho = (int)(t % p.Ho);
+        const int n = (int)(t / p.Ho);
+        const int hi = min((int)floorf(ho * p.sh), p.Hi - 1);      // torch "nearest": floor(dst * in/out)
+        const int wi = min((int)floorf(wo * p.sw), p.Wi - 1);
+        yout[i] = __ldg(xin + (((long long)n * p.Hi + hi) * p.Wi + wi) * p.CV + cv);
+    }
+}
+
 static int gn_plan(GnParams& p, int es) {
     const int VN = 16 / es;
-    p.CV = p.C / VN;
+    // slice the channels over blockIdx.z until one pixel row of a slice fits one CTA (<= 512 vectors);
+    // slices must hold whole groups and whole 16-byte vectors
+    int K = 1;
+    for (; K <= 64; ++K) {
+        if (p.C % K) continue;
+        const int cs = p.C / K;
+        if (cs % p.cpg == 0 && cs % VN == 0 && cs / VN <= kGnMaxThreads) break;
+    }
+    if (K > 64) return -1;
+    p.Cs = p.C / K;
+    p.CV = p.Cs / VN;
     int R = kGnMaxThreads / p.CV;
     if (R < 1) return -1;
     if (R > 32) R = 32;
@@ -197,28 +289,31 @@ int64_t rd_groupnorm_workspace_bytes(int N, int G) {
     return (int64_t)N * kGnMaxChunks * (G > 0 ? G : 1) * 2 * (int64_t)sizeof(double);
 }
 
-int rd_groupnorm_nhwc(const void* x, void* y, const void* gamma, const void* beta, int N, int HW, int C, int G, float eps,
-                      int act, rd_dtype dtype, void* workspace, int64_t workspace_bytes, void* stream) {
+int rd_groupnorm_nhwc(const void* x, void* y, const void* gamma, const void* beta, const void* pre_add, int N, int HW,
+                      int C, int G, float eps, int act, rd_dtype dtype, void* workspace, int64_t workspace_bytes,
+                      void* stream) {
     RD_CHECK_ARG(x && y && workspace, "NULL pointer");
     RD_CHECK_ARG(N >= 1 && HW >= 1 && C >= 1 && G >= 1 && G <= 64 && C % G == 0, "bad shape N=%d HW=%d C=%d G=%d", N, HW, C, G);
     RD_CHECK_ARG(N <= 65535, "N must be <= 65535");
     RD_CHECK_ARG(act == 0 || act == 1, "act must be 0 (none) or 1 (SiLU)");
+    RD_CHECK_ARG(dtype == RD_F32 || dtype == RD_F16 || dtype == RD_BF16, "bad dtype");
     const int es = dtype == RD_F32 ? 4 : 2;
     if (C % (16 / es) != 0) { set_error("C=%d is not a multiple of the 16-byte vector width", C); return RD_ERR_UNSUPPORTED; }
-    RD_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "x / y must be 16-byte aligned");
+    RD_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)pre_add & 15) == 0,
+                 "x / y / pre_add must be 16-byte aligned");
     GnParams p{};
-    p.x = x; p.y = y; p.gamma = gamma; p.beta = beta;
+    p.x = x; p.y = y; p.gamma = gamma; p.beta = beta; p.pre = pre_add;
     p.partial = reinterpret_cast<double*>(workspace);
     p.N = N; p.HW = HW; p.C = C; p.G = G; p.cpg = C / G; p.eps = eps; p.act = act;
-    if (gn_plan(p, es) != 0) { set_error("C=%d too wide for one CTA row", C); return RD_ERR_UNSUPPORTED; }
+    if (gn_plan(p, es) != 0) { set_error("no channel slicing found for C=%d G=%d", C, G); return RD_ERR_UNSUPPORTED; }
     if (workspace_bytes < (int64_t)N * p.chunks * G * 2 * (int64_t)sizeof(double)) {
         set_error("group-norm workspace too small");
         return RD_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int threads = p.CV * p.R;
-    dim3 grid(p.chunks, N);
-    const size_t sm_stats = 2 * (size_t)C * sizeof(double), sm_apply = 2 * (size_t)C * sizeof(float);
+    dim3 grid(p.chunks, N, C / p.Cs);
+    const size_t sm_stats = 2 * (size_t)p.Cs * sizeof(double), sm_apply = 2 * (size_t)p.Cs * sizeof(float);
     switch (dtype) {
         case RD_F32:
             gn_stats_kernel<float><<<grid, threads, sm_stats, st>>>(p);
@@ -228,13 +323,58 @@ int rd_groupnorm_nhwc(const void* x, void* y, const void* gamma, const void* bet
             gn_stats_kernel<__half><<<grid, threads, sm_stats, st>>>(p);
             gn_apply_kernel<__half><<<grid, threads, sm_apply, st>>>(p);
             break;
-        case RD_BF16:
+        default:
             gn_stats_kernel<__nv_bfloat16><<<grid, threads, sm_stats, st>>>(p);
             gn_apply_kernel<__nv_bfloat16><<<grid, threads, sm_apply, st>>>(p);
             break;
-        default: set_error("bad dtype"); return RD_ERR_BAD_ARG;
     }
     RD_LAUNCH_CHECK("gn kernels");
+    return RD_OK;
+}
+
+int rd_bias_residual_nhwc(const void* x, const void* bias, const void* vec, const void* residual, void* y, int N, int HW,
+                          int C, rd_dtype dtype, void* stream) {
+    RD_CHECK_ARG(x && y, "NULL pointer");
+    RD_CHECK_ARG(N >= 1 && N <= 65535 && HW >= 1 && C >= 1, "bad shape");
+    RD_CHECK_ARG(dtype == RD_F32 || dtype == RD_F16 || dtype == RD_BF16, "bad dtype");
+    const int es = dtype == RD_F32 ? 4 : 2, VN = 16 / es;
+    if (C % VN != 0) { set_error("C=%d is not a multiple of the 16-byte vector width", C); return RD_ERR_UNSUPPORTED; }
+    RD_CHECK_ARG((((uintptr_t)x | (uintptr_t)y | (uintptr_t)bias | (uintptr_t)vec | (uintptr_t)residual) & 15) == 0,
+                 "pointers must be 16-byte aligned");
+    AddParams p{};
+    p.x = x; p.bias = bias; p.vec = vec; p.res = residual; p.y = y; p.N = N; p.HW = HW; p.C = C; p.CV = C / VN;
+    int cvt = p.CV < 256 ? p.CV : 256;          // column vectors per pass
+    while (p.CV % cvt) --cvt;
+    int R = 256 / cvt; if (R < 1) R = 1; if (R > 32) R = 32;
+    p.R = R;
+    int rows = 8 * R;
+    int chunks = (HW + rows - 1) / rows;
+    if (chunks > 4096) { chunks = 4096; rows = (HW + chunks - 1) / chunks; chunks = (HW + rows - 1) / rows; }
+    p.chunks = chunks; p.rows_per_chunk = rows;
+    dim3 grid(chunks, N);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case RD_F32: bias_residual_kernel<float><<<grid, cvt * R, 0, st>>>(p); break;
+        case RD_F16: bias_residual_kernel<__half><<<grid, cvt * R, 0, st>>>(p); break;
+        default:     bias_residual_kernel<__nv_bfloat16><<<grid, cvt * R, 0, st>>>(p); break;
+    }
+    RD_LAUNCH_CHECK("bias_residual_kernel");
+    return RD_OK;
+}
+
+int rd_upsample_nearest_nhwc(const void* x, void* y, int N, int Hi, int Wi, int Ho, int Wo, int C, rd_dtype dtype,
+                             void* stream) {
+    RD_CHECK_ARG(x && y && N >= 1 && Hi >= 1 && Wi >= 1 && Ho >= 1 && Wo >= 1 && C >= 1, "bad argument");
+    RD_CHECK_ARG(dtype == RD_F32 || dtype == RD_F16 || dtype == RD_BF16, "bad dtype");
+    const int es = dtype == RD_F32 ? 4 : 2, VN = 16 / es;
+    if (C % VN != 0) { set_error("C=%d is not a multiple of the 16-byte vector width", C); return RD_ERR_UNSUPPORTED; }
+    RD_CHECK_ARG((((uintptr_t)x | (uintptr_t)y) & 15) == 0, "pointers must be 16-byte aligned");
+    UpParams p{x, y, N, Hi, Wi, Ho, Wo, C / VN, (float)Hi / (float)Ho, (float)Wi / (float)Wo};
+    const long long total = (long long)N * Ho * Wo * p.CV;
+    long long want = (total + 255) / 256;
+    const int blocks = (int)(want > (long long)num_sms() * 32 ? (long long)num_sms() * 32 : want);
+    upsample_nearest_nhwc_kernel<uint4><<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
+    RD_LAUNCH_CHECK("upsample_nearest_nhwc_kernel");
     return RD_OK;
 }
 

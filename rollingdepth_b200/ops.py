@@ -91,32 +91,73 @@ def renorm_(depth: torch.Tensor, minmax: torch.Tensor) -> torch.Tensor:
     return depth
 
 
-def group_norm_nhwc(x: torch.Tensor, num_groups: int, weight: Optional[torch.Tensor], bias: Optional[torch.Tensor],
-                    eps: float, silu: bool) -> torch.Tensor:
-    """GroupNorm (+SiLU) on a channels-last activation: x is [N, C, H, W] in torch.channels_last memory format
-    or [N, L, C] contiguous.  Returns a tensor with the same shape / memory format."""
-    L.require_cuda(x)
+def _nhwc_dims(x: torch.Tensor):
     if x.dim() == 4:
-        N, Cc, H, W = x.shape
+        N, C, H, W = x.shape
         if not x.is_contiguous(memory_format=torch.channels_last):
-            raise L.RdError("group_norm_nhwc needs a channels_last tensor")
-        HW = H * W
-        y = torch.empty_like(x, memory_format=torch.channels_last)
-    elif x.dim() == 3:
-        N, HW, Cc = x.shape
+            raise L.RdError("expected a channels_last [N, C, H, W] tensor")
+        return N, H * W, C
+    if x.dim() == 3:
         if not x.is_contiguous():
-            raise L.RdError("group_norm_nhwc needs a contiguous [N, L, C] tensor")
-        y = torch.empty_like(x)
-    else:
-        raise L.RdError("group_norm_nhwc expects a 3-D or 4-D tensor")
+            raise L.RdError("expected a contiguous [N, L, C] tensor")
+        return x.shape[0], x.shape[1], x.shape[2]
+    raise L.RdError("expected a 3-D [N, L, C] or 4-D channels_last tensor")
+
+
+def _opt(t: Optional[torch.Tensor], dtype) -> Optional[torch.Tensor]:
+    return None if t is None else t.to(dtype).contiguous()
+
+
+def group_norm_nhwc(x: torch.Tensor, num_groups: int, weight: Optional[torch.Tensor], bias: Optional[torch.Tensor],
+                    eps: float, silu: bool, pre_add: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """act(GroupNorm(x + pre_add[n, c])) on a channels-last activation ([N, C, H, W] in torch.channels_last
+    memory format or [N, L, C] contiguous); same shape / memory format out."""
+    L.require_cuda(x)
+    N, HW, Cc = _nhwc_dims(x)
+    y = torch.empty_like(x)          # preserve_format keeps channels_last
     lib = L.lib()
     ws_bytes = lib.rd_groupnorm_workspace_bytes(N, num_groups)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
-    g = weight.to(x.dtype) if weight is not None else None
-    b = bias.to(x.dtype) if bias is not None else None
-    code = lib.rd_groupnorm_nhwc(L.ptr(x), L.ptr(y), L.ptr(g) if g is not None else None, L.ptr(b) if b is not None else None,
-                                 N, HW, Cc, int(num_groups), float(eps), 1 if silu else 0, L.dtype_code(x.dtype),
-                                 L.ptr(ws), ws_bytes, L.stream_ptr(x.device))
+    g, b, pre = _opt(weight, x.dtype), _opt(bias, x.dtype), _opt(pre_add, x.dtype)
+    if pre is not None and tuple(pre.shape) != (N, Cc):
+        raise L.RdError(f"pre_add must be [{N}, {Cc}], got {tuple(pre.shape)}")
+    P = lambda t: L.ptr(t) if t is not None else None
+    code = lib.rd_groupnorm_nhwc(L.ptr(x), L.ptr(y), P(g), P(b), P(pre), N, HW, Cc, int(num_groups), float(eps),
+                                 1 if silu else 0, L.dtype_code(x.dtype), L.ptr(ws), ws_bytes, L.stream_ptr(x.device))
     L.check(code, "rd_groupnorm_nhwc")
     L.count_launches(2)
+    return y
+
+
+def bias_residual_nhwc(x: torch.Tensor, bias: Optional[torch.Tensor] = None, vec: Optional[torch.Tensor] = None,
+                       residual: Optional[torch.Tensor] = None, inplace: bool = True) -> torch.Tensor:
+    """x + bias[c] + vec[n, c] + residual in one pass (channels-last)."""
+    L.require_cuda(x)
+    N, HW, Cc = _nhwc_dims(x)
+    if residual is not None:
+        if residual.shape != x.shape or residual.dtype != x.dtype:
+            raise L.RdError("residual must match x")
+        _nhwc_dims(residual)
+    y = x if inplace else torch.empty_like(x)
+    b, v = _opt(bias, x.dtype), _opt(vec, x.dtype)
+    P = lambda t: L.ptr(t) if t is not None else None
+    code = L.lib().rd_bias_residual_nhwc(L.ptr(x), P(b), P(v), P(residual), L.ptr(y), N, HW, Cc, L.dtype_code(x.dtype),
+                                         L.stream_ptr(x.device))
+    L.check(code, "rd_bias_residual_nhwc")
+    L.count_launches(1)
+    return y
+
+
+def upsample_nearest_nhwc(x: torch.Tensor, size) -> torch.Tensor:
+    """F.interpolate(x, size=size, mode="nearest") for a channels_last [N, C, H, W] tensor."""
+    L.require_cuda(x)
+    if x.dim() != 4 or not x.is_contiguous(memory_format=torch.channels_last):
+        raise L.RdError("expected a channels_last [N, C, H, W] tensor")
+    N, Cc, H, W = x.shape
+    Ho, Wo = int(size[0]), int(size[1])
+    y = torch.empty((N, Cc, Ho, Wo), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+    code = L.lib().rd_upsample_nearest_nhwc(L.ptr(x), L.ptr(y), N, H, W, Ho, Wo, Cc, L.dtype_code(x.dtype),
+                                            L.stream_ptr(x.device))
+    L.check(code, "rd_upsample_nearest_nhwc")
+    L.count_launches(1)
     return y

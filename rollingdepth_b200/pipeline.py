@@ -84,13 +84,13 @@ class RollingDepthPipeline:
         key = (self.device, self.dtype)
         if self._tuned_for == key:
             return
-        from .sd2.layers import GroupNormAct
+        from .sd2.layers import BiasConv2d, GroupNormAct, ResnetBlock2D, Upsample2D
         for m in (self.unet, self.vae):
             if self.channels_last:
                 m.to(memory_format=torch.channels_last)
             for sub in m.modules():
-                if isinstance(sub, GroupNormAct):
-                    sub.fused = self.fused_norm
+                if isinstance(sub, (GroupNormAct, BiasConv2d, ResnetBlock2D, Upsample2D)):
+                    sub.fused = self.fused_norm and self.channels_last
         self._tuned_for = key
 
     def enable_sharding(self, group=None) -> "RollingDepthPipeline":

@@ -48,6 +48,28 @@ class TimestepEmbedding(nn.Module):
         return self.linear_2(self.act(self.linear_1(sample)))
 
 
+# --------------------------------------------------------------------------- convolution with a fused bias pass
+def _is_cl(x: torch.Tensor) -> bool:
+    return x.dim() == 4 and x.is_contiguous(memory_format=torch.channels_last)
+
+
+class BiasConv2d(nn.Conv2d):
+    """`nn.Conv2d` (same parameters / state-dict keys).  With `fused = True` on CUDA the convolution runs
+    bias-free on cuDNN (NHWC) and the bias is added by one vectorised in-place pass of our own kernel
+    (rd_bias_residual_nhwc) instead of torch's broadcast add, which is not vectorised for NHWC tensors."""
+
+    fused = False
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.fused and x.is_cuda and self.bias is not None and self.out_channels % (16 // x.element_size()) == 0:
+            y = F.conv2d(x, self.weight, None, self.stride, self.padding, self.dilation, self.groups)
+            if _is_cl(y):
+                from .. import ops
+                return ops.bias_residual_nhwc(y, bias=self.bias)
+            return y + self.bias.view(1, -1, 1, 1)
+        return super().forward(x)
+
+
 # --------------------------------------------------------------------------- GroupNorm (+SiLU)
 class GroupNormAct(nn.GroupNorm):
     """`nn.GroupNorm` (same parameters / state-dict keys) with an optional trailing SiLU.
@@ -238,10 +260,10 @@ class Transformer2DModel(nn.Module):
         inner = heads * dim_head
         self.use_linear_projection = use_linear_projection
         self.norm = GroupNormAct(norm_num_groups, in_channels, eps=1e-6)
-        self.proj_in = nn.Linear(in_channels, inner) if use_linear_projection else nn.Conv2d(in_channels, inner, 1)
+        self.proj_in = nn.Linear(in_channels, inner) if use_linear_projection else BiasConv2d(in_channels, inner, 1)
         self.transformer_blocks = nn.ModuleList(
             [BasicTransformerBlock(inner, heads, dim_head, cross_attention_dim) for _ in range(num_layers)])
-        self.proj_out = nn.Linear(inner, in_channels) if use_linear_projection else nn.Conv2d(inner, in_channels, 1)
+        self.proj_out = nn.Linear(inner, in_channels) if use_linear_projection else BiasConv2d(inner, in_channels, 1)
 
     def forward(self, x, encoder_hidden_states=None, num_view=None):
         b, c, h, w = x.shape
@@ -274,16 +296,40 @@ class ResnetBlock2D(nn.Module):
                  eps: float = 1e-5, output_scale_factor: float = 1.0):
         super().__init__()
         self.norm1 = GroupNormAct(groups, in_channels, eps=eps, act=True)      # GroupNorm -> SiLU (:338-339)
-        self.conv1 = nn.Conv2d(in_channels, out_channels, 3, padding=1)
+        self.conv1 = BiasConv2d(in_channels, out_channels, 3, padding=1)
         self.time_emb_proj = nn.Linear(temb_channels, out_channels) if temb_channels is not None else None
         self.norm2 = GroupNormAct(groups, out_channels, eps=eps, act=True)
         self.dropout = nn.Dropout(0.0)
-        self.conv2 = nn.Conv2d(out_channels, out_channels, 3, padding=1)
+        self.conv2 = BiasConv2d(out_channels, out_channels, 3, padding=1)
         self.nonlinearity = nn.SiLU()
-        self.conv_shortcut = nn.Conv2d(in_channels, out_channels, 1) if in_channels != out_channels else None
+        self.conv_shortcut = BiasConv2d(in_channels, out_channels, 1) if in_channels != out_channels else None
         self.output_scale_factor = output_scale_factor
+        self.fused = False
+
+    def _forward_fused(self, x, temb):
+        """Same arithmetic with the element-wise passes folded away: conv1's bias and the projected time
+        embedding enter GroupNorm-2 as a per-(sample, channel) pre-add, conv2's bias (+ shortcut bias) and the
+        skip connection are one pass (resnet.py:338-376)."""
+        from .. import ops
+        if not _is_cl(x):
+            x = x.contiguous(memory_format=torch.channels_last)
+        h = F.conv2d(self.norm1(x), self.conv1.weight, None, padding=1)
+        pre = self.conv1.bias[None].expand(x.shape[0], -1)
+        if self.time_emb_proj is not None and temb is not None:
+            pre = self.time_emb_proj(self.nonlinearity(temb)) + self.conv1.bias
+        h = ops.group_norm_nhwc(h, self.norm2.num_groups, self.norm2.weight, self.norm2.bias, self.norm2.eps, True, pre_add=pre)
+        h = F.conv2d(h, self.conv2.weight, None, padding=1)
+        bias = self.conv2.bias
+        if self.conv_shortcut is not None:
+            x = F.conv2d(x, self.conv_shortcut.weight, None)
+            bias = bias + self.conv_shortcut.bias
+        out = ops.bias_residual_nhwc(h, bias=bias, residual=x)
+        return out if self.output_scale_factor == 1.0 else out / self.output_scale_factor
 
     def forward(self, x, temb=None):
+        if (self.fused and x.is_cuda and x.dim() == 4 and self.norm2._fusable(x)
+                and _is_cl(self.conv1.weight) and self.conv1.weight.shape[2] == 3):
+            return self._forward_fused(x, temb)
         h = self.conv1(self.norm1(x))
         if self.time_emb_proj is not None and temb is not None:
             h = h + self.time_emb_proj(self.nonlinearity(temb))[:, :, None, None]
@@ -298,7 +344,7 @@ class Downsample2D(nn.Module):
     def __init__(self, channels: int, padding: int = 1):
         super().__init__()
         self.padding = padding
-        self.conv = nn.Conv2d(channels, channels, 3, stride=2, padding=padding)
+        self.conv = BiasConv2d(channels, channels, 3, stride=2, padding=padding)
 
     def forward(self, x):
         if self.padding == 0:
@@ -309,9 +355,14 @@ class Downsample2D(nn.Module):
 class Upsample2D(nn.Module):
     def __init__(self, channels: int):
         super().__init__()
-        self.conv = nn.Conv2d(channels, channels, 3, padding=1)
+        self.conv = BiasConv2d(channels, channels, 3, padding=1)
+        self.fused = False
 
     def forward(self, x, output_size=None):
+        if self.fused and x.is_cuda and _is_cl(x) and x.shape[1] % (16 // x.element_size()) == 0:
+            from .. import ops
+            size = tuple(output_size) if output_size is not None else (2 * x.shape[2], 2 * x.shape[3])
+            return self.conv(ops.upsample_nearest_nhwc(x, size))
         if output_size is None:
             x = F.interpolate(x, scale_factor=2.0, mode="nearest")
         else:

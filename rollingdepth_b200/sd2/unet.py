@@ -15,7 +15,7 @@ from typing import Dict, Optional, Sequence, Tuple, Union
 import torch
 import torch.nn as nn
 
-from .layers import (Attention, Downsample2D, GroupNormAct, ResnetBlock2D, TimestepEmbedding, Transformer2DModel, Upsample2D,
+from .layers import (Attention, BiasConv2d, Downsample2D, GroupNormAct, ResnetBlock2D, TimestepEmbedding, Transformer2DModel, Upsample2D,
                      timestep_embedding)
 
 SD2_UNET_CONFIG = dict(
@@ -111,7 +111,7 @@ class UNet2DConditionModel(nn.Module):
         nb = len(block_out_channels)
         heads = (heads,) * nb if isinstance(heads, int) else tuple(heads)
         temb = block_out_channels[0] * 4
-        self.conv_in = nn.Conv2d(in_channels, block_out_channels[0], 3, padding=1)
+        self.conv_in = BiasConv2d(in_channels, block_out_channels[0], 3, padding=1)
         self.time_embedding = TimestepEmbedding(block_out_channels[0], temb)
 
         self.down_blocks = nn.ModuleList()
@@ -139,7 +139,7 @@ class UNet2DConditionModel(nn.Module):
 
         self.conv_norm_out = GroupNormAct(norm_num_groups, block_out_channels[0], eps=1e-5, act=True)
         self.conv_act = nn.SiLU()
-        self.conv_out = nn.Conv2d(block_out_channels[0], out_channels, 3, padding=1)
+        self.conv_out = BiasConv2d(block_out_channels[0], out_channels, 3, padding=1)
 
     # ------------------------------------------------------------------ processor registry (unet_2d_condition.py:697-753)
     @property

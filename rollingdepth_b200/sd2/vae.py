@@ -15,7 +15,7 @@ from typing import Sequence
 import torch
 import torch.nn as nn
 
-from .layers import Attention, Downsample2D, GroupNormAct, ResnetBlock2D, Upsample2D
+from .layers import Attention, BiasConv2d, Downsample2D, GroupNormAct, ResnetBlock2D, Upsample2D
 
 SD_VAE_CONFIG = dict(in_channels=3, out_channels=3, latent_channels=4, block_out_channels=(128, 256, 512, 512),
                      layers_per_block=2, norm_num_groups=32)
@@ -66,7 +66,7 @@ class _DecBlock(nn.Module):
 class Encoder(nn.Module):
     def __init__(self, in_channels, out_channels, block_out_channels: Sequence[int], layers_per_block, groups, double_z=True):
         super().__init__()
-        self.conv_in = nn.Conv2d(in_channels, block_out_channels[0], 3, padding=1)
+        self.conv_in = BiasConv2d(in_channels, block_out_channels[0], 3, padding=1)
         self.down_blocks = nn.ModuleList()
         cout = block_out_channels[0]
         for i, c in enumerate(block_out_channels):
@@ -75,7 +75,7 @@ class Encoder(nn.Module):
         self.mid_block = _VaeMid(block_out_channels[-1], groups, block_out_channels[-1])
         self.conv_norm_out = GroupNormAct(groups, block_out_channels[-1], eps=1e-6, act=True)
         self.conv_act = nn.SiLU()
-        self.conv_out = nn.Conv2d(block_out_channels[-1], 2 * out_channels if double_z else out_channels, 3, padding=1)
+        self.conv_out = BiasConv2d(block_out_channels[-1], 2 * out_channels if double_z else out_channels, 3, padding=1)
 
     def forward(self, x):
         x = self.conv_in(x)
@@ -89,7 +89,7 @@ class Decoder(nn.Module):
     def __init__(self, in_channels, out_channels, block_out_channels: Sequence[int], layers_per_block, groups):
         super().__init__()
         rev = list(reversed(block_out_channels))
-        self.conv_in = nn.Conv2d(in_channels, rev[0], 3, padding=1)
+        self.conv_in = BiasConv2d(in_channels, rev[0], 3, padding=1)
         self.mid_block = _VaeMid(rev[0], groups, rev[0])
         self.up_blocks = nn.ModuleList()
         cout = rev[0]
@@ -98,7 +98,7 @@ class Decoder(nn.Module):
             self.up_blocks.append(_DecBlock(cin, cout, layers_per_block + 1, groups, i != len(rev) - 1))
         self.conv_norm_out = GroupNormAct(groups, rev[-1], eps=1e-6, act=True)
         self.conv_act = nn.SiLU()
-        self.conv_out = nn.Conv2d(rev[-1], out_channels, 3, padding=1)
+        self.conv_out = BiasConv2d(rev[-1], out_channels, 3, padding=1)
 
     def forward(self, z):
         x = self.conv_in(z)
@@ -117,8 +117,8 @@ class AutoencoderKL(nn.Module):
                                       norm_num_groups=norm_num_groups, scaling_factor=scaling_factor)
         self.encoder = Encoder(in_channels, latent_channels, block_out_channels, layers_per_block, norm_num_groups, True)
         self.decoder = Decoder(latent_channels, out_channels, block_out_channels, layers_per_block, norm_num_groups)
-        self.quant_conv = nn.Conv2d(2 * latent_channels, 2 * latent_channels, 1)
-        self.post_quant_conv = nn.Conv2d(latent_channels, latent_channels, 1)
+        self.quant_conv = BiasConv2d(2 * latent_channels, 2 * latent_channels, 1)
+        self.post_quant_conv = BiasConv2d(latent_channels, latent_channels, 1)
 
     @property
     def dtype(self):

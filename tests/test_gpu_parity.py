@@ -378,7 +378,8 @@ def test_coalign_recovers_known_affine():
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
 @pytest.mark.parametrize("shape", [(3, 128, 37, 53), (2, 320, 27, 48), (1, 1920, 14, 24), (5, 512, 54, 96), (2, 2560, 7, 12)])
 @pytest.mark.parametrize("act", [False, True])
-def test_groupnorm_nhwc_matches_torch_fp32(shape, dtype, act):
+@pytest.mark.parametrize("pre", [False, True])
+def test_groupnorm_nhwc_matches_torch_fp32(shape, dtype, act, pre):
     """Floating-point kernel: compared with a plain PyTorch fp32 reference of the same op."""
     from rollingdepth_b200 import ops
     dev = _dev()
@@ -388,8 +389,10 @@ def test_groupnorm_nhwc_matches_torch_fp32(shape, dtype, act):
     x = x.contiguous(memory_format=torch.channels_last)
     wt = (1 + 0.2 * torch.randn(C, generator=g)).to(dtype).to(dev)
     bs = (0.3 * torch.randn(C, generator=g)).to(dtype).to(dev)
-    y = ops.group_norm_nhwc(x, 32, wt, bs, 1e-6, act)
-    ref = torch.nn.functional.group_norm(x.float(), 32, wt.float(), bs.float(), 1e-6)
+    pv = (torch.randn(N, C, generator=g) * 0.5).to(dtype).to(dev) if pre else None
+    y = ops.group_norm_nhwc(x, 32, wt, bs, 1e-6, act, pre_add=pv)
+    xin = x.float() if not pre else (x.float() + pv.float()[:, :, None, None]).to(dtype).float()
+    ref = torch.nn.functional.group_norm(xin, 32, wt.float(), bs.float(), 1e-6)
     if act:
         ref = torch.nn.functional.silu(ref.to(dtype).float())
     assert y.shape == x.shape and y.is_contiguous(memory_format=torch.channels_last)
@@ -398,24 +401,61 @@ def test_groupnorm_nhwc_matches_torch_fp32(shape, dtype, act):
     assert float(err) <= tol, float(err)
     # [N, L, C] entry (attention processors)
     x3 = x.permute(0, 2, 3, 1).reshape(N, H * W, C)
-    y3 = ops.group_norm_nhwc(x3, 32, wt, bs, 1e-6, act)
+    y3 = ops.group_norm_nhwc(x3, 32, wt, bs, 1e-6, act, pre_add=pv)
     assert torch.equal(y3.reshape(N, H, W, C).permute(0, 3, 1, 2), y)
 
 
 def test_fused_modules_match_plain_torch_modules():
     """The SD2 host modules with NHWC weights + fused norms against the same modules in plain torch."""
     import model_utils as mu
-    from rollingdepth_b200.sd2.layers import GroupNormAct
+    from rollingdepth_b200.sd2.unet import UNet2DConditionModel
     from rollingdepth_b200.sd2.vae import AutoencoderKL
     dev = _dev()
     vae = mu.deterministic_init_(AutoencoderKL(**{k: v for k, v in mu.TINY_VAE.items() if not k.endswith("block_types")}).eval(), seed=2)
-    vae = vae.to(dev).half()
-    z = torch.randn(3, 4, 20, 24, device=dev).half()
-    with torch.no_grad():
-        ref = vae.decoder(vae.post_quant_conv(z))
-        vae.to(memory_format=torch.channels_last)
-        for m in vae.modules():
-            if isinstance(m, GroupNormAct):
-                m.fused = True
-        out = vae.decoder(vae.post_quant_conv(z))
-    assert float((out.float() - ref.float()).abs().max()) <= 2e-2 * float(ref.float().abs().max())
+    unet = mu.deterministic_init_(UNet2DConditionModel(**mu.TINY_UNET).eval(), seed=1)
+
+    def fuse(m):
+        m.to(memory_format=torch.channels_last)
+        for sub in m.modules():
+            if hasattr(sub, "fused"):
+                sub.fused = True
+
+    for dtype, tol in ((torch.float32, 2e-4), (torch.float16, 2e-2)):
+        vae = vae.to(dev, dtype)
+        unet = unet.to(dev, dtype)
+        for sub in list(vae.modules()) + list(unet.modules()):
+            if hasattr(sub, "fused"):
+                sub.fused = False
+        z = torch.randn(3, 4, 21, 24, device=dev, dtype=dtype)
+        x = torch.randn(3, 8, 9, 14, device=dev, dtype=dtype)
+        ctx = torch.randn(1, 2, 32, device=dev, dtype=dtype)
+        img = torch.rand(2, 3, 24, 40, device=dev, dtype=dtype) * 2 - 1
+        t = torch.full((3,), 500, device=dev)
+        with torch.no_grad():
+            torch.backends.cudnn.allow_tf32 = False
+            ref_d = vae.decoder(vae.post_quant_conv(z))
+            ref_e = vae.quant_conv(vae.encoder(img))
+            ref_u = unet(x, t, encoder_hidden_states=ctx, num_view=3).sample
+            fuse(vae); fuse(unet)
+            out_d = vae.decoder(vae.post_quant_conv(z))
+            out_e = vae.quant_conv(vae.encoder(img))
+            out_u = unet(x, t, encoder_hidden_states=ctx, num_view=3).sample
+        for o, r in ((out_d, ref_d), (out_e, ref_e), (out_u, ref_u)):
+            assert float((o.float() - r.float()).abs().max()) <= tol * max(1.0, float(r.float().abs().max()))
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
+def test_bias_residual_and_upsample_nhwc(dtype):
+    from rollingdepth_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(3, 320, 13, 17, generator=g).to(dtype).to(dev).contiguous(memory_format=torch.channels_last)
+    r = torch.randn(3, 320, 13, 17, generator=g).to(dtype).to(dev).contiguous(memory_format=torch.channels_last)
+    b = torch.randn(320, generator=g).to(dtype).to(dev)
+    v = torch.randn(3, 320, generator=g).to(dtype).to(dev)
+    y = ops.bias_residual_nhwc(x, bias=b, vec=v, residual=r, inplace=False)
+    ref = (x.float() + b.float().view(1, -1, 1, 1) + v.float()[:, :, None, None] + r.float()).to(dtype)
+    assert float((y.float() - ref.float()).abs().max()) <= (4e-3 if dtype == torch.float16 else 1e-6)
+    for size in ((26, 34), (27, 33), (14, 24)):
+        up = ops.upsample_nearest_nhwc(x, size)
+        assert torch.equal(up, torch.nn.functional.interpolate(x, size=size, mode="nearest"))
