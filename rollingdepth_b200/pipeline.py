@@ -209,7 +209,9 @@ class RollingDepthPipeline:
         self._tune_modules()
 
         # ----------------- Initial prediction -----------------
-        input_frames = input_frames.to(self.dtype).to(device, non_blocking=True)      # :263
+        # :263 converts on the host and then copies; copying first (async from pinned memory) and rounding to the
+        # pipeline dtype on the device gives the same values (one round-to-nearest either way) without the CPU pass
+        input_frames = input_frames.to(device, non_blocking=True).to(self.dtype)
         rgb_latent = self.encode_rgb(input_frames, max_batch_size=max_vae_bs, verbose=verbose, sharded=True)
         if self.empty_text_embed is None:
             self.encode_empty_text()
@@ -256,13 +258,24 @@ class RollingDepthPipeline:
         else:
             depth_pred = depth_coaligned
 
-        # ----------------- Output (:347-354) -----------------
-        return RollingDepthOutput(
-            input_rgb=input_frames.detach().cpu().squeeze(0) / 2.0 + 0.5,
-            depth_pred=depth_pred.detach().cpu().squeeze(0),
-            snippet_ls=[snippet.detach().cpu() for snippet in snippet_pred_ls],
-            depth_coaligned=depth_coaligned.detach().cpu().squeeze(0),
+        # ----------------- Output (:347-354): everything to the host -----------------
+        # asynchronous copies into pinned host tensors (torch's caching host allocator), one sync at the end
+        out = RollingDepthOutput(
+            input_rgb=self._to_host(input_frames.squeeze(0) / 2.0 + 0.5),
+            depth_pred=self._to_host(depth_pred.squeeze(0)),
+            snippet_ls=[self._to_host(snippet) for snippet in snippet_pred_ls],
+            depth_coaligned=self._to_host(depth_coaligned.squeeze(0)),
         )
+        torch.cuda.current_stream(device).synchronize()
+        return out
+
+    @staticmethod
+    def _to_host(t: torch.Tensor) -> torch.Tensor:
+        if not t.is_cuda:
+            return t
+        host = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+        host.copy_(t, non_blocking=True)
+        return host
 
     # ------------------------------------------------------------------ initial snippet inference (:356-463)
     def init_snippet_infer(self, rgb_latent, init_noise, dilations, cap_dilation, snippet_lengths, init_infer_steps,
