@@ -262,7 +262,7 @@ def run_ours(args):
                 "avg_launch_ms": avg, "share_of_step": sum(sum(v) for v in by_shape.values()) / ms,
                 "flops_per_launch": flops}
     finite = bool(torch.isfinite(out.depth_pred.float()).all())
-    h2d = host_frames.numel() * (2 if dtype != torch.float32 else 4)
+    h2d = host_frames.numel() * host_frames.element_size()    # fp32 frames are copied, rounded on the device
     d2h = sum(t.numel() * t.element_size() for t in [out2.input_rgb, out2.depth_pred, out2.depth_coaligned] + list(out2.snippet_ls))
     line = None
     if rank == 0:

@@ -60,7 +60,9 @@ int rd_device_arch(void);
  * `flags`: 0 = default kernel; see RD_XATTN_* below (debug / A-B switches).
  */
 #define RD_XATTN_P_VIA_SMEM 1   /* stage P through shared memory instead of TMEM (SS-mode PV MMA) */
-#define RD_XATTN_EXP_F16X2 2    /* packed half2 exp2 for the softmax numerator (fp16/bf16 only) */
+/* share of the softmax exponentials evaluated by a degree-3 polynomial on the FMA pipes instead of MUFU.EX2
+ * (the MUFU pipe is the first ceiling at head_dim 64): every n-th score pair; n = 1 disables, 0 = tuned default */
+#define RD_XATTN_POLY(n) (((n) & 0xF) << 8)
 int rd_xattn_fwd(const void* q, const void* k, const void* v, void* o,
                  int B, int H, int Sq, int Sk, int D,
                  int64_t q_sb, int64_t q_ss, int64_t q_sh,

@@ -73,8 +73,26 @@ __device__ __forceinline__ float ex2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+__device__ __forceinline__ float max3(float a, float b, float c) {
+    float y;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));   // FMNMX3 on sm_100
+    return y;
+}
+// 2^x on the FMA/ALU pipes (the MUFU pipe, 16 results/clk/SM, is the first ceiling of head_dim-64 attention):
+// round-to-nearest split x = xi + xf, xf in [-0.5, 0.5], degree-3 minimax polynomial for 2^xf
+// (max relative error 7.5e-5, below the fp16/bf16 rounding of P), exponent patched in with integer arithmetic.
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -125.0f);
+    const float t = x + 12582912.0f;            // 1.5 * 2^23: the integer part lands in the low mantissa bits
+    const float xf = x - (t - 12582912.0f);
+    float p = fmaf(0.05517164617776871f, xf, 0.2426111251115799f);
+    p = fmaf(p, xf, 0.6932609677314758f);
+    p = fmaf(p, xf, 0.9999280571937561f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 
-template <typename T, bool P_SMEM>
+// POLY: every POLY-th score pair takes the polynomial exp2 path (0 = all on MUFU)
+template <typename T, bool P_SMEM, int POLY>
 __global__ void __launch_bounds__(kThreads, P_SMEM ? 1 : 2)
 xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, const XattnParams prm) {
@@ -208,11 +226,16 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                     for (int i = 0; i < 32; ++i)
                         if (c * 32 + i >= valid) sr[c][i] = 0xff800000u;   // -inf
             }
-            float mt = -INFINITY;
+            // row maximum: 8 independent chains of 3-input max (a single dependent chain of 128 FMNMX is ~500 cycles)
+            float mx[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) mx[q] = -INFINITY;
 #pragma unroll
             for (int c = 0; c < 4; ++c)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) mt = fmaxf(mt, __uint_as_float(sr[c][i]));
+                for (int i = 0; i < 32; i += 2)
+                    mx[(i >> 1) & 7] = max3(mx[(i >> 1) & 7], __uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1]));
+            const float mt = fmaxf(max3(mx[0], mx[1], mx[2]), max3(max3(mx[3], mx[4], mx[5]), mx[6], mx[7]));
             const float m_new = fmaxf(m_used, mt);
 
             if (j > 0) {
@@ -242,16 +265,36 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
             const float mb = m_used * sl2;
             uint32_t pk[2][32];
+            float ls[4] = {0.f, 0.f, 0.f, 0.f};       // independent partial row sums
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                    const float p0 = ex2(fmaf(__uint_as_float(sr[c][i]), sl2, -mb));
-                    const float p1 = ex2(fmaf(__uint_as_float(sr[c][i + 1]), sl2, -mb));
-                    l += p0 + p1;
+                    const float x0 = fmaf(__uint_as_float(sr[c][i]), sl2, -mb);
+                    const float x1 = fmaf(__uint_as_float(sr[c][i + 1]), sl2, -mb);
+                    float p0, p1;
+                    if constexpr (POLY == -1 && std::is_same<T, __half>::value) {
+                        // experiment: half-precision MUFU (MUFU.EX2.F16 per half) on the packed pair
+                        uint32_t h, e;
+                        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
+                        asm("ex2.approx.f16x2 %0, %1;" : "=r"(e) : "r"(h));
+                        const float2 pf = __half22float2(*reinterpret_cast<__half2*>(&e));
+                        ls[(i >> 1) & 3] += pf.x + pf.y;
+                        pk[c >> 1][(c & 1) * 16 + (i >> 1)] = e;
+                        continue;
+                    }
+                    if (POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == POLY - 1) {
+                        p0 = ex2_poly(x0);
+                        p1 = ex2_poly(x1);
+                    } else {
+                        p0 = ex2(x0);
+                        p1 = ex2(x1);
+                    }
+                    ls[(i >> 1) & 3] += p0 + p1;
                     pk[c >> 1][(c & 1) * 16 + (i >> 1)] = PackPair<T>::pack(p0, p1);
                 }
             }
+            l += (ls[0] + ls[1]) + (ls[2] + ls[3]);
             if constexpr (P_SMEM) {
                 // K-major SWIZZLE_128B: two [128 x 64] sub-tiles, 16-byte chunk index XOR (row % 8)
                 uint8_t* prow = smem + XattnSmem::p + (row >> 3) * 1024 + (row & 7) * 128;
@@ -348,22 +391,38 @@ int xattn_f32_launch(const float* q, const float* k, const float* v, float* o, i
                      const int64_t* qs, const int64_t* ks, const int64_t* vs, const int64_t* os, float scale,
                      cudaStream_t st);
 
+template <typename T, bool P_SMEM, int POLY>
+static int launch_k(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const XattnParams& prm, dim3 grid,
+                    cudaStream_t st) {
+    auto kern = xattn_fwd_kernel<T, P_SMEM, POLY>;
+    const int smem = (P_SMEM ? XattnSmem::bytes_smem_variant : XattnSmem::bytes_tmem_variant) + 1024;
+    static bool configured = false;      // per instantiation; cudaFuncSetAttribute is not a stream operation
+    if (!configured) {
+        RD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    kern<<<grid, kThreads, smem, st>>>(mq, mk, mv, prm);
+    RD_LAUNCH_CHECK("xattn_fwd_kernel");
+    return RD_OK;
+}
+
+constexpr int kDefaultPoly = 4;
+
 template <typename T>
 static int launch_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const XattnParams& prm, dim3 grid,
                     int flags, cudaStream_t st) {
-    if (flags & RD_XATTN_P_VIA_SMEM) {
-        auto kern = xattn_fwd_kernel<T, true>;
-        const int smem = XattnSmem::bytes_smem_variant + 1024;
-        RD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        kern<<<grid, kThreads, smem, st>>>(mq, mk, mv, prm);
-    } else {
-        auto kern = xattn_fwd_kernel<T, false>;
-        const int smem = XattnSmem::bytes_tmem_variant + 1024;
-        RD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        kern<<<grid, kThreads, smem, st>>>(mq, mk, mv, prm);
+    if (flags & RD_XATTN_P_VIA_SMEM) return launch_k<T, true, 0>(mq, mk, mv, prm, grid, st);
+    int poly = (flags >> 8) & 0xF;       // RD_XATTN_POLY(n): 0 = default, 1 = off, n >= 2 = every n-th pair
+    if (poly == 0) poly = kDefaultPoly;
+    switch (poly) {
+        case 1: return launch_k<T, false, 0>(mq, mk, mv, prm, grid, st);
+        case 2: return launch_k<T, false, 2>(mq, mk, mv, prm, grid, st);
+        case 3: return launch_k<T, false, 3>(mq, mk, mv, prm, grid, st);
+        case 4: return launch_k<T, false, 4>(mq, mk, mv, prm, grid, st);
+        case 6: return launch_k<T, false, 6>(mq, mk, mv, prm, grid, st);
+        case 15: return launch_k<T, false, -1>(mq, mk, mv, prm, grid, st);   // experiment: fp16 MUFU
+        default: set_error("RD_XATTN_POLY(%d) is not instantiated (1, 2, 3, 4, 6)", poly); return RD_ERR_UNSUPPORTED;
     }
-    RD_LAUNCH_CHECK("xattn_fwd_kernel");
-    return RD_OK;
 }
 
 }  // namespace rd

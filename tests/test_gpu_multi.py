@@ -1,0 +1,61 @@
+"""Multi-GPU (snippet-sharded) result invariance: 2 ranks over NCCL vs 1 rank, same inputs (`-m gpu`, needs >= 2 GPUs)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["RD_ROOT"]); sys.path.insert(0, os.path.join(os.environ["RD_ROOT"], "tests"))
+import model_utils as mu
+from rollingdepth_b200.pipeline import RollingDepthPipeline
+from rollingdepth_b200.scheduler import DDIMSchedule
+from rollingdepth_b200.sd2.unet import UNet2DConditionModel
+from rollingdepth_b200.sd2.vae import AutoencoderKL
+rank = int(os.environ["RANK"]); local = int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local); dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+unet = mu.deterministic_init_(UNet2DConditionModel(**mu.TINY_UNET).eval(), seed=1).to(dev).half()
+vae = mu.deterministic_init_(AutoencoderKL(**{k: v for k, v in mu.TINY_VAE.items() if not k.endswith("block_types")}).eval(), seed=2).to(dev).half()
+g = torch.Generator().manual_seed(3)
+frames = torch.rand(1, 14, 3, 48, 64, generator=g) * 2 - 1
+frames = torch.nn.functional.avg_pool2d(frames[0], 5, 1, 2)[None]
+text = torch.randn(1, 2, 32, generator=g).to(dev).half()
+def run(shard):
+    pipe = RollingDepthPipeline(unet, vae, DDIMSchedule(**mu.DDIM_CFG), snippet_batch=2)
+    pipe.empty_text_embed = text
+    if shard: pipe.enable_sharding()
+    return pipe.forward(input_frames=frames, dilations=[1, 3], cap_dilation=True, snippet_lengths=[3], init_infer_steps=[1],
+                        strides=[1], coalign_kwargs=dict(num_iterations=40), refine_step=2, refine_snippet_len=3,
+                        refine_start_dilation=3, generator=torch.Generator().manual_seed(0), verbose=False, max_vae_bs=4,
+                        unload_snippet=False)
+single = run(False)
+sharded = run(True)
+err_c = float((single.depth_coaligned.float() - sharded.depth_coaligned.float()).abs().max())
+err_p = float((single.depth_pred.float() - sharded.depth_pred.float()).abs().max())
+print(f"rank {rank}: coaligned max-abs {err_c:.3e}, depth_pred max-abs {err_p:.3e}", flush=True)
+assert err_c <= 2e-3 and err_p <= 2e-2, (err_c, err_p)
+d0, d1 = (single.depth_pred.float() + 1) / 2, (sharded.depth_pred.float() + 1) / 2
+absrel = float(((d0 - d1).abs() / d0.clamp_min(1e-3)).mean())
+assert absrel <= 1e-3, absrel
+dist.barrier(); dist.destroy_process_group()
+print("rank", rank, "ok", flush=True)
+'''
+
+
+def test_snippet_sharding_two_gpus_matches_single_gpu(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, RD_ROOT=ROOT)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
+                       capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count(" ok") == 2

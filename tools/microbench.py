@@ -57,7 +57,9 @@ def bench_attn(args):
                 cases.append((f"{res}px n={n} L1", n * hw // 4, 10))
     cases += [("fast L0 (768x432 n=3)", 15552, 5), ("fast L1", 3888, 10), ("fast L2", 1008, 20), ("fast mid", 252, 20),
               ("full L0 (1024x576 n=3)", 27648, 5), ("full L1", 6912, 10)]
-    for dtype in (torch.float16, torch.bfloat16):
+    if args.only:
+        cases = [c for c in cases if args.only in c[0]]
+    for dtype in ((torch.float16,) if args.only else (torch.float16, torch.bfloat16)):
         for name, S, H in cases:
             q = torch.randn(1, S, H * 64, device=dev, dtype=dtype).view(1, S, H, 64)
             k = torch.randn(1, S, H * 64, device=dev, dtype=dtype).view(1, S, H, 64)
@@ -94,6 +96,8 @@ def bench_align(args):
     for name, N, H, W, dil, dtype in cfgs:
         if args.small and N > 200:
             continue
+        if args.only and args.only not in name:
+            continue
         al = DepthAligner(device=dev, num_iterations=args.iters)
         # Build the subsampled problem directly on the device (full-resolution 1000-frame snippets would be
         # 15-20 GB); the optimiser only ever sees x_small.  prep / min / merge are timed separately below.
@@ -124,6 +128,8 @@ def bench_align(args):
                               us_per_iter=1e3 * ms / args.iters, MB_per_iter=bytes_iter / 1e6, GBs=gbs,
                               frac_of_hbm=gbs / hbm, peak=hbm, peak_src=src, loss0=float(h[0, 0]), lossN=float(h[-1, 0]),
                               fits_L2=bytes_iter < 126e6)), flush=True)
+    if args.only:
+        return
     # merge / min / prep at full resolution (150 frames, fp16, fast preset)
     N, H, W, dil, dtype = 150, 432, 768, [1, 25], torch.float16
     al = DepthAligner(device=dev)
@@ -145,5 +151,6 @@ if __name__ == "__main__":
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--flags", type=int, nargs="+", default=[0])
+    ap.add_argument("--only", default="")
     a = ap.parse_args()
     (bench_attn if a.what == "attn" else bench_align)(a)
