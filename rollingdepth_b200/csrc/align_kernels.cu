@@ -151,14 +151,14 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepParams pp, const float* d
 // =============================================================================================
 // The fused optimisation pass
 // =============================================================================================
-constexpr int kPassThreads = 128;
-constexpr int kPassV = 2;                 // pixels per thread per step
-constexpr int kPassItersPerChunk = 4;     // target steps per (frame, chunk) work item
+constexpr int kPassThreads = 256;
+constexpr int kPassV = 2;                 // pixels per thread per step (one 4- or 8-byte shared-memory load)
+constexpr int kPassSmemBudget = 98304;    // staged bytes per CTA (two CTAs per SM)
 constexpr int kFrameStats = 8;            // sum|target|, sum|tdep|, L1, L2, tmin, tmax, pad, pad
 
 struct PassParams {
     const void* x;
-    int G, w, N, P, P_pad, R, C, n_total, steps_per_frame;
+    int G, w, N, P, P_pad, R, C, n_total, px_per_chunk;
     int d[RD_MAX_GROUPS], n[RD_MAX_GROUPS], row0[RD_MAX_GROUPS];
     int f_begin;
     int apply_update;
@@ -181,19 +181,53 @@ __device__ __forceinline__ void adam_update(float& theta, float& m, float& v, fl
     theta = theta - __fdiv_rn(p.step_size * m, denom);
 }
 
-template <typename T, int V>
-__device__ __forceinline__ void load_px(const T* ptr, float* out) {
-    static_assert(V == 2, "V == 2 only");
+__device__ __forceinline__ uint32_t pass_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+// 1-D bulk asynchronous copy global -> shared (TMA engine, no registers, completion on an mbarrier)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(pass_smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(pass_smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ float rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // one MUFU.RCP, <= 1 ulp
+    return y;
+}
+// x with the sign of r (r = +0 counts as positive; exact zeros only occur for single-contribution frames,
+// which are handled separately)
+__device__ __forceinline__ float with_sign_of(float x, float r) {
+    return __int_as_float(__float_as_int(x) ^ (__float_as_int(r) & 0x80000000));
+}
+
+template <typename T>
+__device__ __forceinline__ void lds_px2(const T* p, float& a, float& b) {
     if constexpr (sizeof(T) == 4) {
-        const uint2 u = ldg_stream8(ptr);
-        out[0] = __uint_as_float(u.x);
-        out[1] = __uint_as_float(u.y);
+        const float2 v = *reinterpret_cast<const float2*>(p);
+        a = v.x; b = v.y;
     } else {
-        const uint32_t u = ldg_stream4(ptr);
+        const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
         const T* h = reinterpret_cast<const T*>(&u);
-        out[0] = Cvt<T>::to_f(h[0]);
-        out[1] = Cvt<T>::to_f(h[1]);
+        a = Cvt<T>::to_f(h[0]); b = Cvt<T>::to_f(h[1]);
     }
+}
+
+// Sum NVAL per-thread values over the 32 lanes of a warp with 31 shuffles per 32 values (butterfly transpose):
+// afterwards lane L holds the warp total of value index bitrev-free mapping idx(L) = L for the first 32 slots.
+template <int NSLOT>   // NSLOT = 32
+__device__ __forceinline__ float warp_transpose_sum(float (&a)[NSLOT], int lane) {
+#pragma unroll
+    for (int k = NSLOT / 2; k >= 1; k >>= 1) {
+        const bool hi = (lane & k) != 0;
+#pragma unroll
+        for (int i = 0; i < k; ++i) {
+            const float send = hi ? a[i] : a[i + k];
+            const float keep = hi ? a[i + k] : a[i];
+            a[i] = keep + __shfl_xor_sync(0xffffffffu, send, k);
+        }
+    }
+    return a[0];   // total of slot `lane` (slot index bits are consumed MSB-first, matching the lane bits)
 }
 
 template <int RM>
@@ -202,73 +236,74 @@ struct PassAcc {
     float fa, fb, l1, l2, tmin, tmax;
 };
 
-template <int RM, int V, bool MASK>
-__device__ __forceinline__ void pass_step(PassAcc<RM>& acc, const float (&xv)[RM][V], const int (&rows)[RM],
-                                          const float (&sc)[RM], const float (&tc)[RM], float cntf, int nvalid_px) {
-    float inv[RM][V];
-    float sy[V], si[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) { sy[v] = 0.f; si[v] = 0.f; }
-#pragma unroll
-    for (int c = 0; c < RM; ++c) {
-        if (rows[c] >= 0) {
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                const float y = fmaf(sc[c], xv[c][v], tc[c]);
-                const float iv = __frcp_rn(fmaxf(y, 1e-3f));
-                inv[c][v] = iv;
-                sy[v] += y;
-                si[v] += iv;
-            }
-        }
-    }
-    float tg[V], td[V];
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-        tg[v] = __fdiv_rn(sy[v], cntf);
-        td[v] = __fdiv_rn(si[v], cntf);
-        const bool ok = !MASK || (v < nvalid_px);
-        if (ok) {
-            acc.fa += fabsf(tg[v]);
-            acc.fb += fabsf(td[v]);
-            acc.tmin = fminf(acc.tmin, tg[v]);
-            acc.tmax = fmaxf(acc.tmax, tg[v]);
-        }
-    }
+// One step = two adjacent pixels (q0, q0 + 1) of every contribution.  ALLV: all RM contributions are present
+// (no predicates); TAIL: only pixel q0 is real (the odd last pixel of a frame).
+template <typename T, int RM, bool ALLV, bool TAIL>
+__device__ __forceinline__ void pass_step2(PassAcc<RM>& acc, const T* stage, int pitch, int q0, const bool (&valid)[RM],
+                                           const float (&sc)[RM], const float (&tc)[RM], float cntf, float rcnt, bool single) {
+    float xv[RM][2], iv[RM][2];
+    float sy0 = 0.f, sy1 = 0.f, si0 = 0.f, si1 = 0.f;
 #pragma unroll
     for (int c = 0; c < RM; ++c) {
-        if (rows[c] >= 0) {
+        if (ALLV || valid[c]) {
+            lds_px2<T>(stage + (size_t)c * pitch + q0, xv[c][0], xv[c][1]);
+            const float y0 = fmaf(sc[c], xv[c][0], tc[c]), y1 = fmaf(sc[c], xv[c][1], tc[c]);
+            iv[c][0] = rcp_fast(fmaxf(y0, 1e-3f));
+            iv[c][1] = rcp_fast(fmaxf(y1, 1e-3f));
+            sy0 += y0; sy1 += y1;
+            si0 += iv[c][0]; si1 += iv[c][1];
+        }
+    }
+    // target = sum / cnt: reciprocal product + one Newton step (correctly rounded quotient)
+    float tg0 = sy0 * rcnt, tg1 = sy1 * rcnt, td0 = si0 * rcnt, td1 = si1 * rcnt;
+    tg0 = fmaf(fmaf(-cntf, tg0, sy0), rcnt, tg0);
+    tg1 = fmaf(fmaf(-cntf, tg1, sy1), rcnt, tg1);
+    td0 = fmaf(fmaf(-cntf, td0, si0), rcnt, td0);
+    td1 = fmaf(fmaf(-cntf, td1, si1), rcnt, td1);
+    if (TAIL) {
+        acc.fa += fabsf(tg0);
+        acc.fb += fabsf(td0);
+        acc.tmin = fminf(acc.tmin, tg0);
+        acc.tmax = fmaxf(acc.tmax, tg0);
+    } else {
+        acc.fa += fabsf(tg0) + fabsf(tg1);
+        acc.fb += fabsf(td0) + fabsf(td1);
+        acc.tmin = fminf(acc.tmin, fminf(tg0, tg1));
+        acc.tmax = fmaxf(acc.tmax, fmaxf(tg0, tg1));
+    }
+    if (single) return;     // y == target exactly: zero data-term gradient (sign(0) = 0) and zero loss
 #pragma unroll
-            for (int v = 0; v < V; ++v) {
-                const bool ok = !MASK || (v < nvalid_px);
-                if (ok) {
-                    const float x = xv[c][v];
-                    const float y = fmaf(sc[c], x, tc[c]);
-                    const float r1 = y - tg[v];
-                    const float sg = (r1 > 0.f ? 1.f : 0.f) - (r1 < 0.f ? 1.f : 0.f);
-                    acc.l1 += fabsf(r1);
-                    acc.A0[c] += sg;
-                    acc.A1[c] = fmaf(sg, x, acc.A1[c]);
-                    const float iv = inv[c][v];
-                    const float r2 = iv - td[v];
-                    const float sd = (r2 > 0.f ? 1.f : 0.f) - (r2 < 0.f ? 1.f : 0.f);
-                    acc.l2 += fabsf(r2);
-                    const float wg = (y >= 1e-3f) ? sd * iv * iv : 0.f;
-                    acc.D0[c] += wg;
-                    acc.D1[c] = fmaf(wg, x, acc.D1[c]);
-                }
+    for (int c = 0; c < RM; ++c) {
+        if (ALLV || valid[c]) {
+#pragma unroll
+            for (int v = 0; v < (TAIL ? 1 : 2); ++v) {
+                const float x = xv[c][v];
+                const float y = fmaf(sc[c], x, tc[c]);
+                const float r1 = y - (v == 0 ? tg0 : tg1);
+                acc.l1 += fabsf(r1);
+                acc.A0[c] += with_sign_of(1.0f, r1);
+                acc.A1[c] += with_sign_of(x, r1);
+                const float in = iv[c][v];
+                const float r2 = in - (v == 0 ? td0 : td1);
+                acc.l2 += fabsf(r2);
+                const float wg = (y >= 1e-3f) ? with_sign_of(in * in, r2) : 0.f;
+                acc.D0[c] += wg;
+                acc.D1[c] = fmaf(wg, x, acc.D1[c]);
             }
         }
     }
 }
 
 template <typename T, int RM>
-__global__ void __launch_bounds__(kPassThreads) coalign_pass_kernel(const PassParams p) {
+__global__ void __launch_bounds__(kPassThreads, 2) coalign_pass_kernel(const PassParams p) {
     constexpr int V = kPassV;
     constexpr int NV = 4 * RM + kFrameStats;
+    constexpr int NROUND = (4 * RM + 4 + 31) / 32;       // summed values: 4 per contribution + fa, fb, l1, l2
+    extern __shared__ __align__(128) unsigned char pass_smem[];
+    __shared__ __align__(8) uint64_t sh_bar;
     __shared__ int sh_row[RM];
     __shared__ float sh_s[RM], sh_t[RM], sh_soft[RM];
-    __shared__ float sh_red[kPassThreads / 32][NV];
+    __shared__ float sh_red[kPassThreads / 32][NROUND * 32 + 2];
     __shared__ float sh_tot[NV];
     __shared__ int sh_last;
 
@@ -276,13 +311,39 @@ __global__ void __launch_bounds__(kPassThreads) coalign_pass_kernel(const PassPa
     const int ch = blockIdx.x;
     const int f = p.f_begin + blockIdx.y;
     const int R = p.R, nt = p.n_total;
+    const int px0 = ch * p.px_per_chunk;
+    const int npx = min(p.P_pad, px0 + p.px_per_chunk) - px0;     // staged pixels (multiple of 8)
+    const int nvalid = min(p.P, px0 + npx) - px0;                 // of which real pixels
+    T* stage = reinterpret_cast<T*>(pass_smem);                   // [R][px_per_chunk]
 
-    // ---------------- prologue: parameters of the <= R snippets touching this frame ----------
-    if (tid < RM) {
+    // ---------------- kick off the bulk copies of this (frame, chunk): nothing below depends on them yet
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pass_smem_u32(&sh_bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        uint32_t total = 0;
+        for (int c = 0; c < R; ++c) {
+            const int g = c / p.w, j = c - g * p.w;
+            const int k = f - j * p.d[g];
+            if (k >= 0 && k < p.n[g]) total += (uint32_t)(npx * sizeof(T));
+        }
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pass_smem_u32(&sh_bar)), "r"(total) : "memory");
+        for (int c = 0; c < R; ++c) {
+            const int g = c / p.w, j = c - g * p.w;
+            const int k = f - j * p.d[g];
+            if (k >= 0 && k < p.n[g]) {
+                const T* src = reinterpret_cast<const T*>(p.x) + ((size_t)(p.row0[g] + k) * p.w + j) * p.P_pad + px0;
+                bulk_g2s(stage + (size_t)c * p.px_per_chunk, src, (uint32_t)(npx * sizeof(T)), &sh_bar);
+            }
+        }
+    }
+
+    // ---------------- prologue: parameters of the <= R snippets touching this frame (overlaps the copies)
+    if (tid >= 32 && tid < 32 + RM) {
+        const int c = tid - 32;
         int row = -1;
         float s = 0.f, t = 0.f, soft = 0.f;
-        if (tid < R) {
-            const int g = tid / p.w, j = tid - g * p.w;
+        if (c < R) {
+            const int g = c / p.w, j = c - g * p.w;
             const int d = p.d[g];
             const int k = f - j * d;
             if (k >= 0 && k < p.n[g]) {
@@ -317,10 +378,10 @@ __global__ void __launch_bounds__(kPassThreads) coalign_pass_kernel(const PassPa
                 }
             }
         }
-        sh_row[tid] = row;
-        sh_s[tid] = s;
-        sh_t[tid] = t;
-        sh_soft[tid] = soft;
+        sh_row[c] = row;
+        sh_s[c] = s;
+        sh_t[c] = t;
+        sh_soft[c] = soft;
     }
     __syncthreads();
     if (ch == 0 && tid == 0) {
@@ -329,72 +390,99 @@ __global__ void __launch_bounds__(kPassThreads) coalign_pass_kernel(const PassPa
         p.hist_frame[(size_t)f * 4 + 1] = soft;
     }
 
-    int rows[RM];
+    bool valid[RM];
     float sc[RM], tc[RM];
-    const T* xp[RM];
     int cnt = 0;
 #pragma unroll
     for (int c = 0; c < RM; ++c) {
-        rows[c] = sh_row[c];
+        valid[c] = sh_row[c] >= 0;
         sc[c] = sh_s[c];
         tc[c] = sh_t[c];
-        const int j = c % p.w;
-        xp[c] = reinterpret_cast<const T*>(p.x) + ((size_t)(rows[c] < 0 ? 0 : rows[c]) * p.w + j) * p.P_pad;
-        cnt += rows[c] >= 0;
+        cnt += valid[c];
     }
     const float cntf = (float)cnt;
+    const float rcnt = __fdiv_rn(1.f, cntf);
+    const bool single = cnt <= 1;       // y == target exactly: the data term has zero gradient (sign(0) = 0)
 
+    // ---------------- wait for the staged rows
+    {
+        uint32_t ok = 0;
+        int spins = 0;
+        do {
+            asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0, 100000;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                         : "=r"(ok) : "r"(pass_smem_u32(&sh_bar)) : "memory");
+            if (!ok && ++spins > 4000000) __trap();
+        } while (!ok);
+    }
+
+    // ---------------- main loop: two pixels per thread per step, everything from shared memory.
+    // Interior frames have all R contributions (no per-contribution branches); the odd last pixel of a frame
+    // is handled by a masked step of one thread.
     PassAcc<RM> acc;
 #pragma unroll
     for (int c = 0; c < RM; ++c) { acc.A0[c] = acc.A1[c] = acc.D0[c] = acc.D1[c] = 0.f; }
     acc.fa = acc.fb = acc.l1 = acc.l2 = 0.f;
     acc.tmin = INFINITY;
     acc.tmax = -INFINITY;
+    const int npair = nvalid & ~1;
+    if (cnt == R && RM == R) {
+        for (int q0 = tid * V; q0 < npair; q0 += kPassThreads * V)
+            pass_step2<T, RM, true, false>(acc, stage, p.px_per_chunk, q0, valid, sc, tc, cntf, rcnt, single);
+    } else {
+        for (int q0 = tid * V; q0 < npair; q0 += kPassThreads * V)
+            pass_step2<T, RM, false, false>(acc, stage, p.px_per_chunk, q0, valid, sc, tc, cntf, rcnt, single);
+    }
+    if ((nvalid & 1) && tid == 0)
+        pass_step2<T, RM, false, true>(acc, stage, p.px_per_chunk, nvalid - 1, valid, sc, tc, cntf, rcnt, single);
+    float (&A0)[RM] = acc.A0; float (&A1)[RM] = acc.A1; float (&D0)[RM] = acc.D0; float (&D1)[RM] = acc.D1;
+    const float fa = acc.fa, fb = acc.fb, l1 = acc.l1, l2 = acc.l2, tmin = acc.tmin, tmax = acc.tmax;
 
-    // ---------------- main loop over this chunk's pixel steps --------------------------------
-    const int base = p.steps_per_frame / p.C, rem = p.steps_per_frame % p.C;
-    const int st0 = ch * base + min(ch, rem);
-    const int st1 = st0 + base + (ch < rem ? 1 : 0);
-    for (int st = st0; st < st1; ++st) {
-        const int p0 = (st * kPassThreads + tid) * V;
-        if (p0 >= p.P) continue;
-        float xv[RM][V];
+    // ---------------- block reduction: butterfly within warps, fixed-order sum across warps
+    const int lane = tid & 31, warp = tid >> 5;
+    {
+        float slot[NROUND][32];
+#pragma unroll
+        for (int r = 0; r < NROUND; ++r)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) slot[r][i] = 0.f;
 #pragma unroll
         for (int c = 0; c < RM; ++c) {
-            if (rows[c] >= 0) load_px<T, V>(xp[c] + p0, xv[c]);
+            slot[(4 * c + 0) / 32][(4 * c + 0) % 32] = A0[c];
+            slot[(4 * c + 1) / 32][(4 * c + 1) % 32] = A1[c];
+            slot[(4 * c + 2) / 32][(4 * c + 2) % 32] = D0[c];
+            slot[(4 * c + 3) / 32][(4 * c + 3) % 32] = D1[c];
         }
-        if (p0 + V <= p.P) pass_step<RM, V, false>(acc, xv, rows, sc, tc, cntf, V);
-        else               pass_step<RM, V, true>(acc, xv, rows, sc, tc, cntf, p.P - p0);
-    }
-
-    // ---------------- block reduction -> part[f][ch][*] ---------------------------------------
-    const int lane = tid & 31, warp = tid >> 5;
+        slot[(4 * RM + 0) / 32][(4 * RM + 0) % 32] = fa;
+        slot[(4 * RM + 1) / 32][(4 * RM + 1) % 32] = fb;
+        slot[(4 * RM + 2) / 32][(4 * RM + 2) % 32] = l1;
+        slot[(4 * RM + 3) / 32][(4 * RM + 3) % 32] = l2;
 #pragma unroll
-    for (int c = 0; c < RM; ++c) {
-        const float a0 = warp_sum(acc.A0[c]), a1 = warp_sum(acc.A1[c]);
-        const float d0 = warp_sum(acc.D0[c]), d1 = warp_sum(acc.D1[c]);
-        if (lane == 0) {
-            sh_red[warp][4 * c + 0] = a0; sh_red[warp][4 * c + 1] = a1;
-            sh_red[warp][4 * c + 2] = d0; sh_red[warp][4 * c + 3] = d1;
+        for (int r = 0; r < NROUND; ++r) {
+            const float tot = warp_transpose_sum<32>(slot[r], lane);
+            // after the butterfly, lane L holds slot index with bits consumed from k = 16 down to 1: index = L
+            sh_red[warp][r * 32 + lane] = tot;
         }
-    }
-    {
-        const float fa = warp_sum(acc.fa), fb = warp_sum(acc.fb), l1 = warp_sum(acc.l1), l2 = warp_sum(acc.l2);
-        const float mn = warp_min(acc.tmin), mx = warp_max(acc.tmax);
-        if (lane == 0) {
-            float* r = &sh_red[warp][4 * RM];
-            r[0] = fa; r[1] = fb; r[2] = l1; r[3] = l2; r[4] = mn; r[5] = mx; r[6] = 0.f; r[7] = 0.f;
-        }
+        const float mn = warp_min(tmin), mx = warp_max(tmax);
+        if (lane == 0) { sh_red[warp][NROUND * 32] = mn; sh_red[warp][NROUND * 32 + 1] = mx; }
     }
     __syncthreads();
     float* part_f = p.part + (size_t)f * p.C * NV;
     if (tid < NV) {
-        float v = sh_red[0][tid];
+        // NV layout: [4*c + {A0,A1,D0,D1}] for c < RM, then fa, fb, l1, l2, tmin, tmax, pad, pad
         const int q = tid - 4 * RM;
+        float v;
+        if (q == 4 || q == 5) {
+            v = sh_red[0][NROUND * 32 + (q - 4)];
+            for (int w = 1; w < kPassThreads / 32; ++w) {
+                const float o = sh_red[w][NROUND * 32 + (q - 4)];
+                v = (q == 4) ? fminf(v, o) : fmaxf(v, o);
+            }
+        } else if (q >= 6) {
+            v = 0.f;
+        } else {
+            v = 0.f;
 #pragma unroll
-        for (int w = 1; w < kPassThreads / 32; ++w) {
-            const float o = sh_red[w][tid];
-            v = (q == 4) ? fminf(v, o) : (q == 5) ? fmaxf(v, o) : v + o;
+            for (int w = 0; w < kPassThreads / 32; ++w) v += sh_red[w][tid];
         }
         if (p.C == 1) sh_tot[tid] = v;
         else part_f[(size_t)ch * NV + tid] = v;
@@ -429,10 +517,10 @@ __global__ void __launch_bounds__(kPassThreads) coalign_pass_kernel(const PassPa
     if (tid < R) {
         float2 gg = make_float2(0.f, 0.f);
         if (sh_row[tid] >= 0) {
-            const float A0 = sh_tot[4 * tid + 0], A1 = sh_tot[4 * tid + 1];
-            const float D0 = sh_tot[4 * tid + 2], D1 = sh_tot[4 * tid + 3];
-            gg.x = p.ls_over_Z * (A1 * ia - p.dlw * D1 * ib);   // d loss / d s  (data term)
-            gg.y = p.ls_over_Z * (A0 * ia - p.dlw * D0 * ib);   // d loss / d t
+            const float a0 = sh_tot[4 * tid + 0], a1 = sh_tot[4 * tid + 1];
+            const float d0 = sh_tot[4 * tid + 2], d1 = sh_tot[4 * tid + 3];
+            gg.x = p.ls_over_Z * (a1 * ia - p.dlw * d1 * ib);   // d loss / d s  (data term)
+            gg.y = p.ls_over_Z * (a0 * ia - p.dlw * d0 * ib);   // d loss / d t
         }
         reinterpret_cast<float2*>(p.gterm_out)[(size_t)f * R + tid] = gg;
     }
@@ -652,7 +740,7 @@ static int check_problem(const rd_coalign_problem* p) {
 
 struct WsLayout {
     size_t theta, gterm_local, gterm_global, part, counter, hist_frame, flags, total;
-    int C, steps_per_frame, RM, NV;
+    int C, px_per_chunk, RM, NV;
 };
 
 static int pick_rm(int R) {
@@ -667,9 +755,15 @@ static WsLayout ws_layout(const rd_coalign_problem* p, int n_iter) {
     const int R = p->G * p->w;
     L.RM = pick_rm(R);
     L.NV = 4 * (L.RM < 0 ? 16 : L.RM) + kFrameStats;
-    L.steps_per_frame = (p->P + kPassThreads * kPassV - 1) / (kPassThreads * kPassV);
-    L.C = (L.steps_per_frame + kPassItersPerChunk - 1) / kPassItersPerChunk;
-    if (L.C < 1) L.C = 1;
+    {   // pixels per (frame, chunk): all R rows of a chunk are staged in shared memory at once
+        const int es = p->dtype == RD_F32 ? 4 : 2;
+        int max_px = kPassSmemBudget / (R * es);
+        max_px &= ~7;
+        if (max_px < 8) max_px = 8;
+        L.C = (p->P_pad + max_px - 1) / max_px;
+        if (L.C < 1) L.C = 1;
+        L.px_per_chunk = (((p->P_pad + L.C - 1) / L.C) + 7) & ~7;
+    }
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };
     L.theta = take(sizeof(float) * 2 * 6 * (size_t)p->n_total);
@@ -685,25 +779,37 @@ static WsLayout ws_layout(const rd_coalign_problem* p, int n_iter) {
 
 struct WsFlags { int single_rank; int n_iter; };
 
+template <typename T, int RM>
+static int launch_pass_k(const PassParams& pp, dim3 grid, cudaStream_t st) {
+    auto kern = coalign_pass_kernel<T, RM>;
+    const int smem = pp.R * pp.px_per_chunk * (int)sizeof(T);
+    static bool configured = false;
+    if (!configured) {
+        RD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPassSmemBudget + 1024));
+        configured = true;
+    }
+    kern<<<grid, kPassThreads, smem, st>>>(pp);
+    RD_LAUNCH_CHECK("coalign_pass_kernel");
+    return RD_OK;
+}
+
 template <typename T>
 static int launch_pass_t(const PassParams& pp, int RM, dim3 grid, cudaStream_t st) {
     switch (RM) {
-        case 4:  coalign_pass_kernel<T, 4><<<grid, kPassThreads, 0, st>>>(pp); break;
-        case 6:  coalign_pass_kernel<T, 6><<<grid, kPassThreads, 0, st>>>(pp); break;
-        case 9:  coalign_pass_kernel<T, 9><<<grid, kPassThreads, 0, st>>>(pp); break;
-        case 12: coalign_pass_kernel<T, 12><<<grid, kPassThreads, 0, st>>>(pp); break;
-        case 16: coalign_pass_kernel<T, 16><<<grid, kPassThreads, 0, st>>>(pp); break;
+        case 4:  return launch_pass_k<T, 4>(pp, grid, st);
+        case 6:  return launch_pass_k<T, 6>(pp, grid, st);
+        case 9:  return launch_pass_k<T, 9>(pp, grid, st);
+        case 12: return launch_pass_k<T, 12>(pp, grid, st);
+        case 16: return launch_pass_k<T, 16>(pp, grid, st);
         default: set_error("unsupported G*w"); return RD_ERR_UNSUPPORTED;
     }
-    RD_LAUNCH_CHECK("coalign_pass_kernel");
-    return RD_OK;
 }
 
 static void fill_pass_params(PassParams& pp, const rd_coalign_problem* p, const rd_coalign_hparams* hp, const WsLayout& L,
                              char* ws, int it, int step, bool single) {
     const int R = p->G * p->w;
     pp.G = p->G; pp.w = p->w; pp.N = p->N; pp.P = p->P; pp.P_pad = p->P_pad; pp.R = R; pp.C = L.C;
-    pp.n_total = p->n_total; pp.steps_per_frame = L.steps_per_frame;
+    pp.n_total = p->n_total; pp.px_per_chunk = L.px_per_chunk;
     for (int g = 0; g < RD_MAX_GROUPS; ++g) { pp.d[g] = p->d[g]; pp.n[g] = p->n[g]; pp.row0[g] = p->row0[g]; }
     pp.apply_update = it > 0;
     // torch.optim.Adam: python-double bias corrections, then fp32 tensor math
