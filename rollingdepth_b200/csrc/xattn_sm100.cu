@@ -18,6 +18,7 @@
 
 #include "common.cuh"
 #include "sm100_ptx.cuh"
+#include "tensormap.cuh"
 
 namespace rd {
 
@@ -273,16 +274,6 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                     const float x0 = fmaf(__uint_as_float(sr[c][i]), sl2, -mb);
                     const float x1 = fmaf(__uint_as_float(sr[c][i + 1]), sl2, -mb);
                     float p0, p1;
-                    if constexpr (POLY == -1 && std::is_same<T, __half>::value) {
-                        // experiment: half-precision MUFU (MUFU.EX2.F16 per half) on the packed pair
-                        uint32_t h, e;
-                        asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(x1), "f"(x0));
-                        asm("ex2.approx.f16x2 %0, %1;" : "=r"(e) : "r"(h));
-                        const float2 pf = __half22float2(*reinterpret_cast<__half2*>(&e));
-                        ls[(i >> 1) & 3] += pf.x + pf.y;
-                        pk[c >> 1][(c & 1) * 16 + (i >> 1)] = e;
-                        continue;
-                    }
                     if (POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == POLY - 1) {
                         p0 = ex2_poly(x0);
                         p1 = ex2_poly(x1);
@@ -353,40 +344,8 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 }
 
 // ---------------------------------------------------------------------------------------------
-// host side: tensor maps through the driver entry point (no link-time dependency on libcuda)
+// host side (tensor maps: tensormap.cuh)
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static PFN_encodeTiled get_encode() {
-    static PFN_encodeTiled fn = nullptr;
-    if (!fn) {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<PFN_encodeTiled>(p);
-    }
-    return fn;
-}
-
-static int make_map(CUtensorMap* m, const void* base, rd_dtype dt, int B, int H, int S, int64_t sb, int64_t ss, int64_t sh) {
-    PFN_encodeTiled enc = get_encode();
-    if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return RD_ERR_CUDA; }
-    const cuuint64_t dims[4] = {(cuuint64_t)kD, (cuuint64_t)S, (cuuint64_t)H, (cuuint64_t)B};
-    if (B == 1) sb = (int64_t)S * ss;   // unused stride; keep it legal
-    if (H == 1) sh = kD;
-    const cuuint64_t strides[3] = {(cuuint64_t)ss * 2, (cuuint64_t)sh * 2, (cuuint64_t)sb * 2};
-    const cuuint32_t box[4] = {kD, kBN, 1, 1};
-    const cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(m, dt == RD_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
-                     const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return RD_ERR_CUDA; }
-    return RD_OK;
-}
-
 int xattn_f32_launch(const float* q, const float* k, const float* v, float* o, int B, int H, int Sq, int Sk,
                      const int64_t* qs, const int64_t* ks, const int64_t* vs, const int64_t* os, float scale,
                      cudaStream_t st);
@@ -406,7 +365,7 @@ static int launch_k(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensor
     return RD_OK;
 }
 
-constexpr int kDefaultPoly = 4;
+constexpr int kDefaultPoly = 1;   // polynomial path off: measured slower on B200 (attention log)
 
 template <typename T>
 static int launch_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const XattnParams& prm, dim3 grid,
@@ -420,7 +379,6 @@ static int launch_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensor
         case 3: return launch_k<T, false, 3>(mq, mk, mv, prm, grid, st);
         case 4: return launch_k<T, false, 4>(mq, mk, mv, prm, grid, st);
         case 6: return launch_k<T, false, 6>(mq, mk, mv, prm, grid, st);
-        case 15: return launch_k<T, false, -1>(mq, mk, mv, prm, grid, st);   // experiment: fp16 MUFU
         default: set_error("RD_XATTN_POLY(%d) is not instantiated (1, 2, 3, 4, 6)", poly); return RD_ERR_UNSUPPORTED;
     }
 }
@@ -451,9 +409,9 @@ extern "C" int rd_xattn_fwd(const void* q, const void* k, const void* v, void* o
     RD_CHECK_ARG(((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)v % 16) == 0 && ((uintptr_t)o % 16) == 0,
                  "q/k/v/o must be 16-byte aligned");
     CUtensorMap mq, mk, mv;
-    if (int e = make_map(&mq, q, dtype, B, H, Sq, q_sb, q_ss, q_sh)) return e;
-    if (int e = make_map(&mk, k, dtype, B, H, Sk, k_sb, k_ss, k_sh)) return e;
-    if (int e = make_map(&mv, v, dtype, B, H, Sk, v_sb, v_ss, v_sh)) return e;
+    if (int e = make_qkv_map(&mq, q, dtype, B, H, Sq, q_sb, q_ss, q_sh, kBM)) return e;
+    if (int e = make_qkv_map(&mk, k, dtype, B, H, Sk, k_sb, k_ss, k_sh, kBN)) return e;
+    if (int e = make_qkv_map(&mv, v, dtype, B, H, Sk, v_sb, v_ss, v_sh, kBN)) return e;
     XattnParams prm{};
     prm.o = o; prm.o_sb = o_sb; prm.o_ss = o_ss; prm.o_sh = o_sh;
     prm.Sq = Sq; prm.Sk = Sk; prm.n_kv_tiles = (Sk + kBN - 1) / kBN;
