@@ -304,7 +304,13 @@ if __name__ == "__main__":
     ap.add_argument("--fused-norm", type=int, default=1)
     ap.add_argument("--cudnn-benchmark", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--frames", type=int, default=0,
+                    help="profiling only: shorter clip than the preset (the ncu launch list); NOT a bench configuration")
     a = ap.parse_args()
+    if a.frames:
+        cfg = list(PRESETS[a.preset])
+        cfg[0] = a.frames
+        PRESETS[a.preset] = tuple(cfg)
     if a.impl == "reference":
         run_reference(a)
     else:

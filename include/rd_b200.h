@@ -59,7 +59,6 @@ int rd_device_arch(void);
  * fp32 accumulation; RD_F32 runs the error-compensated fp32 path (|err| <= 1e-4).
  * `flags`: 0 = default kernel; see RD_XATTN_* below (debug / A-B switches).
  */
-#define RD_XATTN_P_VIA_SMEM 1   /* stage P through shared memory instead of TMEM (SS-mode PV MMA) */
 /* share of the softmax exponentials evaluated by a degree-3 polynomial on the FMA pipes instead of MUFU.EX2
  * (the MUFU pipe is the first ceiling at head_dim 64): every n-th score pair; n = 1 disables, 0 = tuned default */
 #define RD_XATTN_POLY(n) (((n) & 0xF) << 8)

@@ -16,7 +16,6 @@ LIB_PATH = os.path.join(_HERE, "librd_b200.so")
 
 RD_F32, RD_F16, RD_BF16 = 0, 1, 2
 RD_MAX_GROUPS, RD_MAX_WINDOW = 8, 8
-XATTN_P_VIA_SMEM = 1
 
 
 def XATTN_POLY(n: int) -> int:

@@ -151,9 +151,12 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepParams pp, const float* d
 // =============================================================================================
 // The fused optimisation pass
 // =============================================================================================
-constexpr int kPassThreads = 256;
+// CTA shape of the pass: the packed accumulators need ~168 registers per thread, i.e. <= 384 threads per SM.
+// cfg 0: 192 threads x 2 CTAs/SM, 96 KB staged each;  cfg 1: 128 threads x 3 CTAs/SM, 64 KB staged each (three-way
+// overlap of the load / compute / reduce phases of consecutive CTAs).  RD_COALIGN_CFG selects at run time (A/B).
+constexpr int kPassThreadsMax = 192;
 constexpr int kPassV = 2;                 // pixels per thread per step (one 4- or 8-byte shared-memory load)
-constexpr int kPassSmemBudget = 98304;    // staged bytes per CTA (two CTAs per SM)
+constexpr int kPassSmemBudgetMax = 98304;
 constexpr int kFrameStats = 8;            // sum|target|, sum|tdep|, L1, L2, tmin, tmax, pad, pad
 
 struct PassParams {
@@ -201,16 +204,55 @@ __device__ __forceinline__ float with_sign_of(float x, float r) {
     return __int_as_float(__float_as_int(x) ^ (__float_as_int(r) & 0x80000000));
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2 take one issue slot for two pixels; a {s, s} operand
+// is encoded as a broadcast scalar register).  The pass is issue-bound, so the two adjacent pixels of a step travel as
+// one 64-bit register pair through every element-wise operation and through the accumulators.
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t bc2(float s) { return pk2(s, s); }
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t fsub2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t fmul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// two adjacent pixels of one staged row as a packed fp32 pair
 template <typename T>
-__device__ __forceinline__ void lds_px2(const T* p, float& a, float& b) {
+__device__ __forceinline__ uint64_t lds_pair(const T* p) {
     if constexpr (sizeof(T) == 4) {
-        const float2 v = *reinterpret_cast<const float2*>(p);
-        a = v.x; b = v.y;
+        return *reinterpret_cast<const uint64_t*>(p);
     } else {
         const uint32_t u = *reinterpret_cast<const uint32_t*>(p);
         const T* h = reinterpret_cast<const T*>(&u);
-        a = Cvt<T>::to_f(h[0]); b = Cvt<T>::to_f(h[1]);
+        return pk2(Cvt<T>::to_f(h[0]), Cvt<T>::to_f(h[1]));
     }
+}
+// (mag | sign bit of r) per lane: mag = 1.0f gives sign(r) with sign(+0) = +1; mag = 0.0f gives +-0
+__device__ __forceinline__ uint64_t signed_mag2(float mag_lo, float mag_hi, uint64_t r) {
+    float r0, r1;
+    upk2(r, r0, r1);
+    return pk2(__int_as_float((__float_as_int(r0) & 0x80000000) | __float_as_int(mag_lo)),
+               __int_as_float((__float_as_int(r1) & 0x80000000) | __float_as_int(mag_hi)));
 }
 
 // Sum NVAL per-thread values over the 32 lanes of a warp with 31 shuffles per 32 values (butterfly transpose):
@@ -231,71 +273,82 @@ __device__ __forceinline__ float warp_transpose_sum(float (&a)[NSLOT], int lane)
 }
 
 template <int RM>
-struct PassAcc {
-    float A0[RM], A1[RM], D0[RM], D1[RM];
-    float fa, fb, l1, l2, tmin, tmax;
+struct PassAcc {                 // every member holds the partial sums of the even and of the odd pixel
+    uint64_t A0[RM], A1[RM], D0[RM], D1[RM];
+    uint64_t fa, fb, l1;
+    float l2, tmin, tmax;
 };
 
 // One step = two adjacent pixels (q0, q0 + 1) of every contribution.  ALLV: all RM contributions are present
-// (no predicates); TAIL: only pixel q0 is real (the odd last pixel of a frame).
+// (no predicates); TAIL: only pixel q0 is real (the odd last pixel of a frame; its neighbour is row padding).
+// ~13 issue slots per (contribution, pixel): LDS.64, FFMA2, 2 FMNMX, 2 MUFU.RCP, 2 FADD2 | FFMA2, FSUB2, 2 LOP3,
+// FFMA2 (L1), FADD2, FFMA2 | FSUB2, 2 FSET, 2 LOP3, 2 FADD (L2), 2 FMUL2, 2 FFMA2   (all per pixel PAIR).
 template <typename T, int RM, bool ALLV, bool TAIL>
 __device__ __forceinline__ void pass_step2(PassAcc<RM>& acc, const T* stage, int pitch, int q0, const bool (&valid)[RM],
                                            const float (&sc)[RM], const float (&tc)[RM], float cntf, float rcnt, bool single) {
-    float xv[RM][2], iv[RM][2];
-    float sy0 = 0.f, sy1 = 0.f, si0 = 0.f, si1 = 0.f;
+    uint64_t xv[RM], iv[RM];
+    uint64_t sy = 0ull, si = 0ull;
 #pragma unroll
     for (int c = 0; c < RM; ++c) {
         if (ALLV || valid[c]) {
-            lds_px2<T>(stage + (size_t)c * pitch + q0, xv[c][0], xv[c][1]);
-            const float y0 = fmaf(sc[c], xv[c][0], tc[c]), y1 = fmaf(sc[c], xv[c][1], tc[c]);
-            iv[c][0] = rcp_fast(fmaxf(y0, 1e-3f));
-            iv[c][1] = rcp_fast(fmaxf(y1, 1e-3f));
-            sy0 += y0; sy1 += y1;
-            si0 += iv[c][0]; si1 += iv[c][1];
+            xv[c] = lds_pair<T>(stage + (size_t)c * pitch + q0);
+            const uint64_t y = ffma2(bc2(sc[c]), xv[c], bc2(tc[c]));
+            float y0, y1;
+            upk2(y, y0, y1);
+            iv[c] = pk2(rcp_fast(fmaxf(y0, 1e-3f)), rcp_fast(fmaxf(y1, 1e-3f)));
+            sy = fadd2(sy, y);
+            si = fadd2(si, iv[c]);
         }
     }
     // target = sum / cnt: reciprocal product + one Newton step (correctly rounded quotient)
-    float tg0 = sy0 * rcnt, tg1 = sy1 * rcnt, td0 = si0 * rcnt, td1 = si1 * rcnt;
-    tg0 = fmaf(fmaf(-cntf, tg0, sy0), rcnt, tg0);
-    tg1 = fmaf(fmaf(-cntf, tg1, sy1), rcnt, tg1);
-    td0 = fmaf(fmaf(-cntf, td0, si0), rcnt, td0);
-    td1 = fmaf(fmaf(-cntf, td1, si1), rcnt, td1);
-    if (TAIL) {
-        acc.fa += fabsf(tg0);
-        acc.fb += fabsf(td0);
-        acc.tmin = fminf(acc.tmin, tg0);
-        acc.tmax = fmaxf(acc.tmax, tg0);
-    } else {
-        acc.fa += fabsf(tg0) + fabsf(tg1);
-        acc.fb += fabsf(td0) + fabsf(td1);
-        acc.tmin = fminf(acc.tmin, fminf(tg0, tg1));
-        acc.tmax = fmaxf(acc.tmax, fmaxf(tg0, tg1));
+    const uint64_t rc = bc2(rcnt), ncnt = bc2(-cntf);
+    uint64_t tg = fmul2(sy, rc), td = fmul2(si, rc);
+    tg = ffma2(ffma2(ncnt, tg, sy), rc, tg);
+    td = ffma2(ffma2(ncnt, td, si), rc, td);
+    {
+        float g0, g1, d0, d1;
+        upk2(tg, g0, g1);
+        upk2(td, d0, d1);
+        if (TAIL) {
+            acc.fa = fadd2(acc.fa, pk2(fabsf(g0), 0.f));
+            acc.fb = fadd2(acc.fb, pk2(fabsf(d0), 0.f));
+            acc.tmin = fminf(acc.tmin, g0);
+            acc.tmax = fmaxf(acc.tmax, g0);
+        } else {
+            acc.fa = fadd2(acc.fa, pk2(fabsf(g0), fabsf(g1)));
+            acc.fb = fadd2(acc.fb, pk2(fabsf(d0), fabsf(d1)));
+            acc.tmin = fminf(acc.tmin, fminf(g0, g1));
+            acc.tmax = fmaxf(acc.tmax, fmaxf(g0, g1));
+        }
     }
     if (single) return;     // y == target exactly: zero data-term gradient (sign(0) = 0) and zero loss
 #pragma unroll
     for (int c = 0; c < RM; ++c) {
         if (ALLV || valid[c]) {
-#pragma unroll
-            for (int v = 0; v < (TAIL ? 1 : 2); ++v) {
-                const float x = xv[c][v];
-                const float y = fmaf(sc[c], x, tc[c]);
-                const float r1 = y - (v == 0 ? tg0 : tg1);
-                acc.l1 += fabsf(r1);
-                acc.A0[c] += with_sign_of(1.0f, r1);
-                acc.A1[c] += with_sign_of(x, r1);
-                const float in = iv[c][v];
-                const float r2 = in - (v == 0 ? td0 : td1);
-                acc.l2 += fabsf(r2);
-                const float wg = (y >= 1e-3f) ? with_sign_of(in * in, r2) : 0.f;
-                acc.D0[c] += wg;
-                acc.D1[c] = fmaf(wg, x, acc.D1[c]);
-            }
+            const uint64_t x = xv[c];
+            const uint64_t y = ffma2(bc2(sc[c]), x, bc2(tc[c]));
+            const uint64_t r1 = fsub2(y, tg);
+            const uint64_t sg = signed_mag2(1.0f, TAIL ? 0.0f : 1.0f, r1);        // sign(y - target)
+            acc.l1 = ffma2(sg, r1, acc.l1);                                        // |r1|
+            acc.A0[c] = fadd2(acc.A0[c], sg);
+            acc.A1[c] = ffma2(sg, x, acc.A1[c]);
+            const uint64_t in = iv[c];
+            const uint64_t r2 = fsub2(in, td);
+            float y0, y1, q0f, q1f;
+            upk2(y, y0, y1);
+            upk2(r2, q0f, q1f);
+            acc.l2 += TAIL ? fabsf(q0f) : fabsf(q0f) + fabsf(q1f);
+            // d(1/clamp(y, 1e-3))/dy = -1/y^2 where y >= 1e-3, else 0 (the minus sign is applied by the caller)
+            const uint64_t sm = signed_mag2(y0 >= 1e-3f ? 1.0f : 0.0f, (!TAIL && y1 >= 1e-3f) ? 1.0f : 0.0f, r2);
+            const uint64_t w = fmul2(in, in);
+            acc.D0[c] = ffma2(sm, w, acc.D0[c]);
+            acc.D1[c] = ffma2(sm, fmul2(w, x), acc.D1[c]);
         }
     }
 }
 
-template <typename T, int RM>
-__global__ void __launch_bounds__(kPassThreads, 2) coalign_pass_kernel(const PassParams p) {
+template <typename T, int RM, int kPassThreads, int kCtasPerSm>
+__global__ void __launch_bounds__(kPassThreads, kCtasPerSm) coalign_pass_kernel(const PassParams p) {
     constexpr int V = kPassV;
     constexpr int NV = 4 * RM + kFrameStats;
     constexpr int NROUND = (4 * RM + 4 + 31) / 32;       // summed values: 4 per contribution + fa, fb, l1, l2
@@ -420,8 +473,9 @@ __global__ void __launch_bounds__(kPassThreads, 2) coalign_pass_kernel(const Pas
     // is handled by a masked step of one thread.
     PassAcc<RM> acc;
 #pragma unroll
-    for (int c = 0; c < RM; ++c) { acc.A0[c] = acc.A1[c] = acc.D0[c] = acc.D1[c] = 0.f; }
-    acc.fa = acc.fb = acc.l1 = acc.l2 = 0.f;
+    for (int c = 0; c < RM; ++c) { acc.A0[c] = acc.A1[c] = acc.D0[c] = acc.D1[c] = 0ull; }
+    acc.fa = acc.fb = acc.l1 = 0ull;
+    acc.l2 = 0.f;
     acc.tmin = INFINITY;
     acc.tmax = -INFINITY;
     const int npair = nvalid & ~1;
@@ -434,8 +488,11 @@ __global__ void __launch_bounds__(kPassThreads, 2) coalign_pass_kernel(const Pas
     }
     if ((nvalid & 1) && tid == 0)
         pass_step2<T, RM, false, true>(acc, stage, p.px_per_chunk, nvalid - 1, valid, sc, tc, cntf, rcnt, single);
-    float (&A0)[RM] = acc.A0; float (&A1)[RM] = acc.A1; float (&D0)[RM] = acc.D0; float (&D1)[RM] = acc.D1;
-    const float fa = acc.fa, fb = acc.fb, l1 = acc.l1, l2 = acc.l2, tmin = acc.tmin, tmax = acc.tmax;
+    auto lanes = [](uint64_t v) { float a, b; upk2(v, a, b); return a + b; };   // even-pixel + odd-pixel partial sums
+    float A0[RM], A1[RM], D0[RM], D1[RM];
+#pragma unroll
+    for (int c = 0; c < RM; ++c) { A0[c] = lanes(acc.A0[c]); A1[c] = lanes(acc.A1[c]); D0[c] = lanes(acc.D0[c]); D1[c] = lanes(acc.D1[c]); }
+    const float fa = lanes(acc.fa), fb = lanes(acc.fb), l1 = lanes(acc.l1), l2 = acc.l2, tmin = acc.tmin, tmax = acc.tmax;
 
     // ---------------- block reduction: butterfly within warps, fixed-order sum across warps
     const int lane = tid & 31, warp = tid >> 5;
@@ -750,6 +807,17 @@ static int pick_rm(int R) {
     return -1;
 }
 
+static int pass_cfg() {
+    static int cfg = -1;
+    if (cfg < 0) {
+        const char* e = getenv("RD_COALIGN_CFG");
+        cfg = e ? atoi(e) : 0;
+        if (cfg < 0 || cfg > 1) cfg = 0;
+    }
+    return cfg;
+}
+static int pass_smem_budget() { return pass_cfg() == 1 ? 65536 : 98304; }
+
 static WsLayout ws_layout(const rd_coalign_problem* p, int n_iter) {
     WsLayout L{};
     const int R = p->G * p->w;
@@ -757,7 +825,7 @@ static WsLayout ws_layout(const rd_coalign_problem* p, int n_iter) {
     L.NV = 4 * (L.RM < 0 ? 16 : L.RM) + kFrameStats;
     {   // pixels per (frame, chunk): all R rows of a chunk are staged in shared memory at once
         const int es = p->dtype == RD_F32 ? 4 : 2;
-        int max_px = kPassSmemBudget / (R * es);
+        int max_px = pass_smem_budget() / (R * es);
         max_px &= ~7;
         if (max_px < 8) max_px = 8;
         L.C = (p->P_pad + max_px - 1) / max_px;
@@ -779,18 +847,23 @@ static WsLayout ws_layout(const rd_coalign_problem* p, int n_iter) {
 
 struct WsFlags { int single_rank; int n_iter; };
 
-template <typename T, int RM>
-static int launch_pass_k(const PassParams& pp, dim3 grid, cudaStream_t st) {
-    auto kern = coalign_pass_kernel<T, RM>;
+template <typename T, int RM, int NT, int NCTA>
+static int launch_pass_c(const PassParams& pp, dim3 grid, cudaStream_t st) {
+    auto kern = coalign_pass_kernel<T, RM, NT, NCTA>;
     const int smem = pp.R * pp.px_per_chunk * (int)sizeof(T);
     static bool configured = false;
     if (!configured) {
-        RD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPassSmemBudget + 1024));
+        RD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPassSmemBudgetMax + 1024));
         configured = true;
     }
-    kern<<<grid, kPassThreads, smem, st>>>(pp);
+    kern<<<grid, NT, smem, st>>>(pp);
     RD_LAUNCH_CHECK("coalign_pass_kernel");
     return RD_OK;
+}
+template <typename T, int RM>
+static int launch_pass_k(const PassParams& pp, dim3 grid, cudaStream_t st) {
+    if (pass_cfg() == 1) return launch_pass_c<T, RM, 128, 3>(pp, grid, st);
+    return launch_pass_c<T, RM, 192, 2>(pp, grid, st);
 }
 
 template <typename T>

@@ -15,6 +15,16 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a fully converged warp (elect.sync).  Role loops run with all 32 lanes in uniform control flow and only
+// the tcgen05 / TMA instruction itself is predicated on the elected lane: the descriptors then live in uniform
+// registers, and a UTCHMMA costs ~4 instructions to issue instead of the ~14 (R2UR.BROADCAST + ELECT loop) that a
+// whole loop under `if (lane == 0)` compiles to.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -41,16 +51,28 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity, ui
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug traps (-> CUDA error on the host) instead of hanging the GPU.
+// Non-suspending probe of the phase (SYNCS.PHASECHK without TRYWAIT): the fast path of every wait.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug traps (-> CUDA error on the host) instead of hanging the GPU.  No printf here:
+// a device-side call would force the ABI register set on the 40-register MMA / TMA warps (setmaxnreg.dec).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifndef RD_MBAR_NO_FASTPATH
+    if (mbar_test_wait(bar, parity)) return;
+#endif
     if (mbar_try_wait(bar, parity)) return;
     int spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > 20000000) {   // each failed try_wait sleeps in hardware; this is >= several seconds
-            printf("rd_b200: mbarrier wait timed out (block %d,%d,%d thread %d bar %u parity %u)\n", blockIdx.x,
-                   blockIdx.y, blockIdx.z, threadIdx.x, smem_u32(bar), parity);
-            __trap();
-        }
+        if (++spins > 20000000) __trap();   // each failed try_wait sleeps in hardware; this is >= several seconds
     }
 }
 
@@ -146,6 +168,15 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "

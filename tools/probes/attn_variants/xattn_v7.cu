@@ -3,25 +3,27 @@
 // (diffusers/src/diffusers/models/attention_processor.py:2251-2253 and :2036-2038).
 //
 // At head_dim 64 one 128x128 score tile costs 512 tensor-pipe cycles (QK^T + PV) but 1024 MUFU cycles
-// (16 exponentials / clk / SM), so the kernel is organised around keeping the MUFU pipe busy:
+// (16 exponentials / clk / SM, tools/probes/pipe_rate.cu), so the kernel is organised around keeping the MUFU pipe
+// busy.  A softmax warp is a strictly in-order chain of long-latency steps (mbarrier wait, TMEM load, row maximum,
+// exponentials, TMEM store, arrive); measured alone it keeps MUFU ~50 % busy however it is software-pipelined
+// (tools/probes/attn_variants/).  The cure is thread-level parallelism: FOUR softmax warps per SM sub-partition.
 //
-// One CTA per SM = TWO 128-row query tiles of one (batch, head) that share every K/V tile.  Warp roles (384 threads;
-// setmaxnreg moves registers from the third warpgroup to the softmax warpgroups: 88 vs 208 per thread):
-//   warps 0-3  softmax of query tile 0, warps 4-7 softmax of query tile 1.  Each thread owns one query row
-//              (= one TMEM lane): S -> registers (tcgen05.ld), row maximum, lazy (thresholded) rescaling of O
-//              in TMEM, exponentials, P -> TMEM as packed fp16/bf16 (tcgen05.st), epilogue O / l -> global.
-//              The two warpgroups run free (two warps per SM sub-partition share its MUFU pipe; while one is
-//              in its TMEM loads / row maximum / barrier traffic the other one has the pipe to itself).  A forced
-//              ping-pong on named barriers (RD_XATTN_PINGPONG) was measured slower and is kept as an A/B switch.
-//   warps 8,9  tcgen05.mma issuers (one elected thread each; warp 8 also owns TMEM), ONE PER QUERY TILE so that the
-//              two softmax warpgroups are decoupled (an in-order issuer shared by both tiles makes each warpgroup wait
-//              for the other one's P): S_t = Q_t K^T (SS mode, both K-major, SWIZZLE_128B), O_t += P_t V (A = P_t
-//              from TMEM, B = V MN-major from shared memory).  K/V stages are released when both issuers committed.
-//   warp 10    TMA producer: both Q tiles once, then K/V tiles of 128 keys through 3-stage rings.
-// TMEM (all 512 columns): S_t fp32 [128 t, +128), O_t fp32 [256 + 64 t, +64), P_t packed 16-bit [384 + 64 t, +64).
-// QK^T of step j+1 is issued as soon as the softmax warps have pulled S_j into registers.
-// Element-wise softmax arithmetic uses the packed fp32x2 instructions of sm_100 (FFMA2 / FADD2), and a tunable
-// share of the exponentials is evaluated by a degree-3 polynomial on the FMA pipe instead of MUFU.EX2.
+// One CTA per SM = FOUR 128-row query tiles of one (batch, head) that share every K/V tile; steps of 64 keys.
+// TMEM (512 columns): query tile t owns columns [128 t, 128 t + 128): S fp32 in [0, 64), overwritten in place by
+// P (packed 16-bit, [0, 32)) once the scores are in registers, and O fp32 in [64, 128).
+// Warp roles (640 threads; setmaxnreg moves registers from the last warpgroup to the softmax warpgroups):
+//   warps 0-15  softmax: warpgroup t = query tile t, one query row (= TMEM lane) per thread.  Per step: wait S_FULL,
+//               S -> registers (tcgen05.ld), row maximum, lazy rescaling of O (only when the running maximum grows
+//               by more than 2^8), exponentials, P -> TMEM (tcgen05.st), arrive P_FULL.  Epilogue O / l -> global.
+//   warp 16     tcgen05.mma issuer (one elected thread) + TMEM owner.  It POLLS the barriers of the four tiles and
+//               issues whatever is ready: O_t += P_t(j) V(j) (A = P from TMEM, B = V MN-major from shared memory)
+//               immediately followed by S_t(j+1) = Q_t K(j+1)^T (SS mode, K-major, SWIZZLE_128B, N = 64).  The tensor
+//               pipe executes one thread's MMAs in order, so S_t(j+1) may overwrite P_t(j) without a wait, and
+//               S_FULL(j+1) also tells the softmax warps that O_t is quiescent.
+//   warp 17     TMA producer: the four Q tiles once, then K/V tiles of 128 keys (two steps) through 3-stage rings.
+// Element-wise softmax arithmetic uses the packed fp32x2 instructions of sm_100 (FFMA2 / FADD2: one issue slot for
+// two results); a share of the exponentials can be evaluated by a degree-3 polynomial on the FMA pipe (RD_XATTN_POLY).
+// Earlier organisations are archived with their measurements under tools/probes/attn_variants/.
 #include <cuda.h>
 #include <math.h>
 #include <type_traits>
@@ -30,20 +32,16 @@
 #include "sm100_ptx.cuh"
 #include "tensormap.cuh"
 
-// internal A/B switches of rd_xattn_fwd `flags` (not part of the public header)
-#define RD_XATTN_PINGPONG 1
-#define RD_XATTN_SINGLE_ISSUER 2
-
 namespace rd {
 
 using namespace ptx;
 
 #ifdef RD_XATTN_TRACE
-// phase cycle counters of softmax warp 0 (summed over CTAs), read by tools/probes/xattn_bench.cu
+// phase cycle counters of the first warp of each softmax warpgroup (summed over CTAs), read by tools/probes/xattn_bench.cu
 __device__ unsigned long long rd_xattn_trace[16];
 #define RD_TRACE_DECL long long tr_t = clock64(); unsigned long long tr_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define RD_TRACE(i) { const long long tr_n = clock64(); tr_acc[i] += (unsigned long long)(tr_n - tr_t); tr_t = tr_n; }
-#define RD_TRACE_FLUSH if ((threadIdx.x & 127) == 0) { const int tr_o = (threadIdx.x >> 7) * 8; for (int tr_i = 0; tr_i < 7; ++tr_i) atomicAdd(&rd_xattn_trace[tr_i], tr_acc[tr_i]); atomicAdd(&rd_xattn_trace[8 + (tr_o >> 3)], 1ull); }
+#define RD_TRACE_FLUSH if ((threadIdx.x & 127) == 0) { for (int tr_i = 0; tr_i < 7; ++tr_i) atomicAdd(&rd_xattn_trace[tr_i], tr_acc[tr_i]); atomicAdd(&rd_xattn_trace[8], 1ull); }
 #else
 #define RD_TRACE_DECL
 #define RD_TRACE(i)
@@ -51,16 +49,18 @@ __device__ unsigned long long rd_xattn_trace[16];
 #endif
 
 constexpr int kBM = 128;       // rows per query tile
-constexpr int kNQ = 2;         // query tiles per CTA
-constexpr int kBN = 128;       // keys per K/V tile
+constexpr int kNQ = 4;         // query tiles per CTA
+constexpr int kBN = 128;       // keys per K/V tile (one TMA box)
+constexpr int kBK = 64;        // keys per softmax / MMA step
 constexpr int kD = 64;         // head dim
 constexpr int kStages = 3;
 constexpr int kTileBytes = kBN * kD * 2;   // 16384
+constexpr int kStepBytes = kBK * kD * 2;   // 8192: second step of a K/V tile
 constexpr int kSoftmaxThreads = kNQ * 128;
-constexpr int kThreads = kSoftmaxThreads + 128;   // third warpgroup: two MMA warps, TMA warp, one idle warp (register donors)
-constexpr int kMmaWarp = kNQ * 4, kTmaWarp = kNQ * 4 + 2;
+constexpr int kThreads = kSoftmaxThreads + 128;   // last warpgroup: MMA warp, TMA warp, two idle warps (register donors)
+constexpr int kMmaWarp = kNQ * 4, kTmaWarp = kNQ * 4 + 1;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColS = 0, kColO = 256, kColP = 384;   // + 128 t, + 64 t, + 64 t
+constexpr uint32_t kColTile = 128, kColS = 0, kColO = 64;
 constexpr float kRescaleThreshold = 8.0f;  // log2 units; p stays <= 2^8
 
 struct XattnSmem {
@@ -74,13 +74,13 @@ struct XattnSmem {
 };
 // barrier indices
 constexpr int Q_FULL = 0, K_FULL = 1, K_EMPTY = K_FULL + kStages, V_FULL = K_EMPTY + kStages, V_EMPTY = V_FULL + kStages,
-              S_FULL = V_EMPTY + kStages, S_FREE = S_FULL + kNQ, P_FULL = S_FREE + kNQ, O_READY = P_FULL + kNQ;
-static_assert(O_READY + kNQ <= 32, "barrier table too small");
+              S_FULL = V_EMPTY + kStages, P_FULL = S_FULL + kNQ, O_DONE = P_FULL + kNQ;
+static_assert(O_DONE + kNQ <= 32, "barrier table too small");
 
 struct XattnParams {
     void* o;
     long long o_sb, o_ss, o_sh;
-    int Sq, Sk, n_kv_tiles;
+    int Sq, Sk, n_kv_tiles, n_steps;
     float scale_log2;   // scale * log2(e)
 };
 
@@ -108,7 +108,7 @@ __device__ __forceinline__ float max3(float a, float b, float c) {
     asm("max.f32 %0, %1, %2, %3;" : "=f"(y) : "f"(a), "f"(b), "f"(c));   // FMNMX3 on sm_100
     return y;
 }
-// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2, two results per issue slot)
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2: one issue slot, two lanes of work)
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
     uint64_t r;
     asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
@@ -134,7 +134,8 @@ __device__ __forceinline__ uint64_t fsub2(uint64_t a, uint64_t b) {
 }
 // 2^x for two values on the FMA/ALU pipes (the MUFU pipe, 16 results/clk/SM, is the first ceiling of head_dim-64
 // attention): round-to-nearest split x = xi + xf, xf in [-0.5, 0.5], degree-3 minimax polynomial for 2^xf (max
-// relative error 7.5e-5, below the fp16/bf16 rounding of P), exponent patched in with one integer multiply-add.
+// relative error 7.5e-5, below the fp16/bf16 rounding of P), exponent patched in with one shift-add.
+// Costs ~10 issue slots per element (pipe_rate probe) against 8 MUFU cycles, so only a small share pays off.
 __device__ __forceinline__ void ex2_poly2(uint64_t x2, float& p0, float& p1) {
     float x0, x1;
     unpack2(x2, x0, x1);
@@ -150,21 +151,34 @@ __device__ __forceinline__ void ex2_poly2(uint64_t x2, float& p0, float& p1) {
     float t0, t1, q0, q1;
     unpack2(t, t0, t1);
     unpack2(p, q0, q1);
-    p0 = __int_as_float(__float_as_int(t0) * (1 << 23) + __float_as_int(q0));
-    p1 = __int_as_float(__float_as_int(t1) * (1 << 23) + __float_as_int(q1));
+    p0 = __int_as_float((__float_as_int(t0) << 23) + __float_as_int(q0));
+    p1 = __int_as_float((__float_as_int(t1) << 23) + __float_as_int(q1));
 }
 
-__device__ __forceinline__ void named_bar_sync(int id, int count) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+// row maximum of one 64-key step: 8 independent chains of 3-input max (one dependent chain would be ~250 cycles)
+__device__ __forceinline__ float row_max64(const uint32_t (&a)[32], const uint32_t (&b)[32]) {
+    float mx[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) mx[q] = max3(__uint_as_float(a[4 * q]), __uint_as_float(a[4 * q + 1]), __uint_as_float(a[4 * q + 2]));
+#pragma unroll
+    for (int q = 0; q < 8; ++q) mx[q] = max3(mx[q], __uint_as_float(a[4 * q + 3]), __uint_as_float(b[4 * q]));
+#pragma unroll
+    for (int q = 0; q < 8; ++q) mx[q] = max3(mx[q], __uint_as_float(b[4 * q + 1]), __uint_as_float(b[4 * q + 2]));
+#pragma unroll
+    for (int q = 0; q < 8; ++q) mx[q] = fmaxf(mx[q], __uint_as_float(b[4 * q + 3]));
+    return fmaxf(max3(mx[0], mx[1], mx[2]), max3(max3(mx[3], mx[4], mx[5]), mx[6], mx[7]));
 }
-__device__ __forceinline__ void named_bar_arrive(int id, int count) {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+
+__device__ __forceinline__ void mask_tail64(uint32_t (&a)[32], uint32_t (&b)[32], int valid) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        if (i >= valid) a[i] = 0xff800000u;        // -inf
+        if (32 + i >= valid) b[i] = 0xff800000u;
+    }
 }
 
 // POLY: every POLY-th score pair takes the polynomial exp2 path (0 = all on MUFU)
-// PINGPONG: the two softmax warpgroups alternate their exponential phases (named barriers 1 and 2)
-// SPLIT: one MMA issuer warp per query tile (false: a single in-order issuer for both tiles)
-template <typename T, int POLY, bool PINGPONG, bool SPLIT>
+template <typename T, int POLY>
 __global__ void __launch_bounds__(kThreads, 1)
 xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, const XattnParams prm) {
@@ -173,24 +187,23 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + XattnSmem::bars);
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(smem + XattnSmem::tmem_ptr);
 
-    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
+    const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int q_blk = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
-    const int n_tiles = prm.n_kv_tiles;
+    const int n_tiles = prm.n_kv_tiles, n_steps = prm.n_steps;
 
     if (threadIdx.x == 0) {
         mbar_init(&bars[Q_FULL], 1);
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&bars[K_FULL + s], 1);
-            mbar_init(&bars[K_EMPTY + s], SPLIT ? kNQ : 1);    // one tcgen05.commit per issuer
+            mbar_init(&bars[K_EMPTY + s], kNQ);    // one tcgen05.commit per query tile
             mbar_init(&bars[V_FULL + s], 1);
-            mbar_init(&bars[V_EMPTY + s], SPLIT ? kNQ : 1);
+            mbar_init(&bars[V_EMPTY + s], kNQ);
         }
-        for (int t = 0; t < kNQ; ++t) {
-            mbar_init(&bars[S_FULL + t], 1);
-            mbar_init(&bars[S_FREE + t], 4);     // one elected lane per softmax warp
-            mbar_init(&bars[P_FULL + t], 4);
-            mbar_init(&bars[O_READY + t], 1);
+        for (int i = 0; i < kNQ; ++i) {
+            mbar_init(&bars[S_FULL + i], 1);
+            mbar_init(&bars[P_FULL + i], 4);       // one elected lane per softmax warp
+            mbar_init(&bars[O_DONE + i], 1);
         }
         mbar_fence_init();
     }
@@ -210,7 +223,7 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
     // (setmaxnreg must dominate the code it applies to: one per role branch, no re-convergence in between)
     if (warp >= kMmaWarp) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         if (warp == kTmaWarp) {
         // ===================================================== TMA producer
         if (lane == 0) {
@@ -228,132 +241,99 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 tma_load_4d(smem + XattnSmem::v + st * kTileBytes, &tm_v, &bars[V_FULL + st], 0, j * kBN, head, batch);
             }
         }
-        } else if (warp == kMmaWarp || (SPLIT && warp == kMmaWarp + 1)) {
-        // ===================================================== MMA issuer(s): query tiles [t_lo, t_hi)
-        // All 32 lanes run the loop (uniform control flow, descriptors in uniform registers); one elected lane issues.
-        {
-            const bool leader = elect_one();
+        } else if (warp == kMmaWarp) {
+        // ===================================================== MMA issuer: polls the four tiles, issues what is ready
+        if (lane == 0) {
             constexpr uint32_t fmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
-            constexpr uint32_t idesc_qk = make_idesc_f16(fmt, 0, 0, kBM, kBN);
+            constexpr uint32_t idesc_qk = make_idesc_f16(fmt, 0, 0, kBM, kBK);
             constexpr uint32_t idesc_pv = make_idesc_f16(fmt, 0, 1, kBM, kD);   // B = V is MN-major
-            const int t_lo = SPLIT ? warp - kMmaWarp : 0, t_hi = SPLIT ? t_lo + 1 : kNQ;
-            const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
-
-            auto issue_qk = [&](int j) {
-                const int st = j % kStages;
-                mbar_wait(&bars[K_FULL + st], (j / kStages) & 1);
-                const uint64_t dk = make_smem_desc_sw128(smem_u32(smem + XattnSmem::k + st * kTileBytes), 16, 1024);
-                for (int t = t_lo; t < t_hi; ++t) {
-                    if (j > 0) mbar_wait(&bars[S_FREE + t], (j - 1) & 1);   // softmax_t(j-1) has S in registers
-                    tc_fence_after();
-                    const uint64_t dq = make_smem_desc_sw128(smem_u32(smem + XattnSmem::q + t * kTileBytes), 16, 1024);
-                    if (leader) {
+            const uint32_t q_addr = smem_u32(smem + XattnSmem::q), k_addr = smem_u32(smem + XattnSmem::k),
+                           v_addr = smem_u32(smem + XattnSmem::v);
+            int pv_j[kNQ];                // next step whose PV has not been issued yet
+            uint32_t s_issued = 0;        // bit t: S(pv_j[t]) has been issued (tile t is waiting for P), else QK^T is next
 #pragma unroll
-                        for (int kk = 0; kk < kD / 16; ++kk)             // +32 bytes along K inside the 128B swizzle row
-                            mma_f16_ss(tm + kColS + t * 128, dq + 2 * kk, dk + 2 * kk, idesc_qk, kk > 0);
-                        if (t == t_hi - 1) mma_commit(&bars[K_EMPTY + st]);
-                        mma_commit(&bars[S_FULL + t]);
-                    }
-                    __syncwarp();
-                }
-            };
-
+            for (int t = 0; t < kNQ; ++t) pv_j[t] = 0;
+            int done = 0;
             mbar_wait(&bars[Q_FULL], 0);
-            issue_qk(0);
-            for (int j = 0; j < n_tiles; ++j) {
-                if (j + 1 < n_tiles) issue_qk(j + 1);
-                const int st = j % kStages;
-                mbar_wait(&bars[V_FULL + st], (j / kStages) & 1);
-                const uint64_t dv = make_smem_desc_sw128(smem_u32(smem + XattnSmem::v + st * kTileBytes), 16, 1024);
-                for (int t = t_lo; t < t_hi; ++t) {
-                    mbar_wait(&bars[P_FULL + t], j & 1);
-                    tc_fence_after();
-                    if (leader) {
+            while (done < kNQ) {
 #pragma unroll
-                        for (int kk = 0; kk < kBN / 16; ++kk)            // V advances 16 key rows = 2048 bytes per K step
-                            mma_f16_ts(tm + kColO + t * 64, tm + kColP + t * 64 + 8 * kk, dv + (uint64_t)(128 * kk),
-                                       idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
-                        if (t == t_hi - 1) mma_commit(&bars[V_EMPTY + st]);
-                        mma_commit(&bars[O_READY + t]);
+                for (int t = 0; t < kNQ; ++t) {
+                    if (s_issued & (1u << t)) {         // S(j) issued: waiting for P(j)
+                        const int j = pv_j[t], tile = j >> 1, st = tile % kStages, b = j & 1;
+                        if (mbar_test_wait(&bars[P_FULL + t], j & 1) && mbar_test_wait(&bars[V_FULL + st], (tile / kStages) & 1)) {
+                            tc_fence_after();
+                            const uint64_t dv = make_smem_desc_sw128(v_addr + st * kTileBytes + b * kStepBytes, 16, 1024);
+#pragma unroll
+                            for (int kk = 0; kk < kBK / 16; ++kk)        // V advances 16 key rows = 2048 bytes per K step
+                                mma_f16_ts(tmem_base + t * kColTile + kColO, tmem_base + t * kColTile + kColS + 8 * kk,
+                                           dv + (uint64_t)(128 * kk), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+                            if (b == 1 || j == n_steps - 1) mma_commit(&bars[V_EMPTY + st]);
+                            if (j == n_steps - 1) { mma_commit(&bars[O_DONE + t]); ++done; }
+                            pv_j[t] = j + 1;
+                            s_issued &= ~(1u << t);
+                        }
                     }
-                    __syncwarp();
+                    if (!(s_issued & (1u << t)) && pv_j[t] < n_steps) {   // PV(i-1) issued (or i = 0): S(i) may overwrite P(i-1)
+                        const int i = pv_j[t], tile = i >> 1, st = tile % kStages, b = i & 1;
+                        if (mbar_test_wait(&bars[K_FULL + st], (tile / kStages) & 1)) {
+                            tc_fence_after();
+                            const uint64_t dq = make_smem_desc_sw128(q_addr + t * kTileBytes, 16, 1024);
+                            const uint64_t dk = make_smem_desc_sw128(k_addr + st * kTileBytes + b * kStepBytes, 16, 1024);
+#pragma unroll
+                            for (int kk = 0; kk < kD / 16; ++kk)         // +32 bytes along K inside the 128B swizzle row
+                                mma_f16_ss(tmem_base + t * kColTile + kColS, dq + 2 * kk, dk + 2 * kk, idesc_qk, kk > 0);
+                            if (b == 1 || i == n_steps - 1) mma_commit(&bars[K_EMPTY + st]);
+                            mma_commit(&bars[S_FULL + t]);
+                            s_issued |= 1u << t;
+                        }
+                    }
                 }
             }
         }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
         // ===================================================== softmax warps (one query row per thread)
         const int t = warp >> 2;                       // query tile of this warpgroup
         const int row = (warp & 3) * 32 + lane;        // row inside the tile = TMEM lane
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-        const uint32_t tS = tmem_base + lane_off + kColS + t * 128, tO = tmem_base + lane_off + kColO + t * 64,
-                       tP = tmem_base + lane_off + kColP + t * 64;
+        const uint32_t tS = tmem_base + lane_off + t * kColTile + kColS, tO = tmem_base + lane_off + t * kColTile + kColO;
         uint64_t* s_full = &bars[S_FULL + t];
-        uint64_t* s_free = &bars[S_FREE + t];
         uint64_t* p_full = &bars[P_FULL + t];
-        uint64_t* o_ready = &bars[O_READY + t];
         const float sl2 = prm.scale_log2;
         const uint64_t sl2_2 = pack2(sl2, sl2);
         float m_used = -INFINITY;   // raw-score units
-        float l = 0.f;
+        uint64_t l2 = 0ull;         // two partial row sums (fp32 x 2)
         RD_TRACE_DECL
-        if (PINGPONG && t == 1) named_bar_arrive(1, kSoftmaxThreads);   // warpgroup 0 goes first
 
-        for (int j = 0; j < n_tiles; ++j) {
+        for (int j = 0; j < n_steps; ++j) {
             mbar_wait(s_full, j & 1);
             tc_fence_after();
             RD_TRACE(0)
-            uint32_t sr[4][32];
-            tmem_ld32(tS + 0, sr[0]);
-            tmem_ld32(tS + 32, sr[1]);
-            tmem_ld32(tS + 64, sr[2]);
-            tmem_ld32(tS + 96, sr[3]);
+            uint32_t sa[32], sb[32];
+            tmem_ld32(tS + 0, sa);
+            tmem_ld32(tS + 32, sb);
             tmem_ld_wait();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(s_free);
             RD_TRACE(1)
-
-            const int valid = prm.Sk - j * kBN;   // keys of this tile that exist
-            if (valid < kBN) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c * 32 + i >= valid) sr[c][i] = 0xff800000u;   // -inf
-            }
-            // row maximum: 8 independent chains of 3-input max (a single dependent chain of 128 FMNMX is ~500 cycles)
-            float mx[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) mx[q] = -INFINITY;
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-                for (int i = 0; i < 32; i += 2)
-                    mx[(i >> 1) & 7] = max3(mx[(i >> 1) & 7], __uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1]));
-            const float mt = fmaxf(max3(mx[0], mx[1], mx[2]), max3(max3(mx[3], mx[4], mx[5]), mx[6], mx[7]));
-            const float m_new = fmaxf(m_used, mt);
-            RD_TRACE(2)
-
-            if (PINGPONG) named_bar_sync(1 + t, kSoftmaxThreads);      // our turn on the MUFU pipe
+            const int valid = prm.Sk - j * kBK;
+            if (valid < kBK) mask_tail64(sa, sb, valid);
+            const float m_new = fmaxf(m_used, row_max64(sa, sb));
+            // S_FULL(j) also means PV(j-1) has completed (in-order tensor pipe): O may be touched here
             if (j > 0) {
-                // P (and O) may only be touched once PV(j-1) has completed
-                mbar_wait(o_ready, (j - 1) & 1);
-                tc_fence_after();
-                RD_TRACE(3)
                 const bool need = (m_new - m_used) * sl2 > kRescaleThreshold;
                 if (__any_sync(0xffffffffu, need)) {
                     const float f = ex2((m_used - m_new) * sl2);
-                    l *= f;
+                    float la, lb;
+                    unpack2(l2, la, lb);
+                    l2 = pack2(la * f, lb * f);
 #pragma unroll 1
-                    for (int c = 0; c < 2; ++c) {           // rare path: keep its register footprint small
-                        uint32_t orr[32];
-                        tmem_ld32(tO + c * 32, orr);
+                    for (int c = 0; c < 4; ++c) {           // rare path: keep its register footprint small
+                        uint32_t orr[16];
+                        tmem_ld16(tO + c * 16, orr);
                         tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * f);
-                        tmem_st32(tO + c * 32, orr);
+                        for (int i = 0; i < 16; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * f);
+                        tmem_st16(tO + c * 16, orr);
                     }
                     tmem_st_wait();
                     m_used = m_new;
@@ -361,75 +341,65 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             } else {
                 m_used = m_new;
             }
-            RD_TRACE(4)
-
+            RD_TRACE(2)
+            // -- exponentials, P(j) -> TMEM over the first half of S(j) (every lane only overwrites its own row)
             const float mb = m_used * sl2;
             const uint64_t nmb2 = pack2(-mb, -mb);
-            uint64_t ls2[2] = {0ull, 0ull};            // independent partial row sums (two fp32 each)
+            uint64_t ls2[2] = {l2, 0ull};
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t pk[32];
+            for (int h = 0; h < 2; ++h) {
+                uint32_t pk[16];
 #pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    const int c = half * 2 + cc;
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const uint64_t x2 = ffma2(pack2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), sl2_2, nmb2);
-                        float p0, p1;
-                        if (POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == POLY - 1) {
-                            ex2_poly2(x2, p0, p1);
-                        } else {
-                            float x0, x1;
-                            unpack2(x2, x0, x1);
-                            p0 = ex2(x0);
-                            p1 = ex2(x1);
-                        }
-                        ls2[(i >> 1) & 1] = fadd2(ls2[(i >> 1) & 1], pack2(p0, p1));
-                        pk[cc * 16 + (i >> 1)] = PackPair<T>::pack(p0, p1);
+                for (int i = 0; i < 32; i += 2) {
+                    const uint32_t r0 = h == 0 ? sa[i] : sb[i], r1 = h == 0 ? sa[i + 1] : sb[i + 1];
+                    const uint64_t x2 = ffma2(pack2(__uint_as_float(r0), __uint_as_float(r1)), sl2_2, nmb2);
+                    float p0, p1;
+                    if (POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == POLY - 1) {
+                        ex2_poly2(x2, p0, p1);
+                    } else {
+                        float x0, x1;
+                        unpack2(x2, x0, x1);
+                        p0 = ex2(x0);
+                        p1 = ex2(x1);
                     }
+                    ls2[(i >> 1) & 1] = fadd2(ls2[(i >> 1) & 1], pack2(p0, p1));
+                    pk[i >> 1] = PackPair<T>::pack(p0, p1);
                 }
-                tmem_st32(tP + half * 32, pk);
+                tmem_st16(tS + h * 16, pk);
             }
-            {
-                float a0, a1, b0, b1;
-                unpack2(ls2[0], a0, a1);
-                unpack2(ls2[1], b0, b1);
-                l += (a0 + a1) + (b0 + b1);
-            }
-            RD_TRACE(5)
+            l2 = fadd2(ls2[0], ls2[1]);
+            RD_TRACE(3)
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
-            if (PINGPONG && !(t == 1 && j == n_tiles - 1)) named_bar_arrive(1 + (t ^ 1), kSoftmaxThreads);
-            RD_TRACE(6)
+            RD_TRACE(4)
         }
         RD_TRACE_FLUSH
 
         // ------------------------------------------------- epilogue: O / l -> global
-        mbar_wait(o_ready, (n_tiles - 1) & 1);
+        mbar_wait(&bars[O_DONE + t], 0);
         tc_fence_after();
-        uint32_t orr[2][32];
-        tmem_ld32(tO + 0, orr[0]);
-        tmem_ld32(tO + 32, orr[1]);
-        tmem_ld_wait();
-        const float inv_l = 1.0f / l;
+        float la, lb;
+        unpack2(l2, la, lb);
+        const float inv_l = 1.0f / (la + lb);
         const int grow = (q_blk * kNQ + t) * kBM + row;
-        if (grow < prm.Sq) {
-            T* dst = reinterpret_cast<T*>(prm.o) + (long long)batch * prm.o_sb + (long long)grow * prm.o_ss +
-                     (long long)head * prm.o_sh;
+        T* dst = reinterpret_cast<T*>(prm.o) + (long long)batch * prm.o_sb + (long long)grow * prm.o_ss + (long long)head * prm.o_sh;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            uint32_t orr[32];
+            tmem_ld32(tO + c * 32, orr);
+            tmem_ld_wait();
+            if (grow < prm.Sq) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                uint4 val;
-                uint32_t w[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int e = c * 8 + i * 2;
-                    w[i] = PackPair<T>::pack(__uint_as_float(orr[e >> 5][e & 31]) * inv_l,
-                                             __uint_as_float(orr[(e + 1) >> 5][(e + 1) & 31]) * inv_l);
+                for (int g = 0; g < 4; ++g) {
+                    uint4 val;
+                    val.x = PackPair<T>::pack(__uint_as_float(orr[8 * g + 0]) * inv_l, __uint_as_float(orr[8 * g + 1]) * inv_l);
+                    val.y = PackPair<T>::pack(__uint_as_float(orr[8 * g + 2]) * inv_l, __uint_as_float(orr[8 * g + 3]) * inv_l);
+                    val.z = PackPair<T>::pack(__uint_as_float(orr[8 * g + 4]) * inv_l, __uint_as_float(orr[8 * g + 5]) * inv_l);
+                    val.w = PackPair<T>::pack(__uint_as_float(orr[8 * g + 6]) * inv_l, __uint_as_float(orr[8 * g + 7]) * inv_l);
+                    *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = val;
                 }
-                val.x = w[0]; val.y = w[1]; val.z = w[2]; val.w = w[3];
-                *reinterpret_cast<uint4*>(dst + c * 8) = val;
             }
         }
         tc_fence_before();
@@ -449,10 +419,10 @@ int xattn_f32_launch(const float* q, const float* k, const float* v, float* o, i
                      const int64_t* qs, const int64_t* ks, const int64_t* vs, const int64_t* os, float scale,
                      cudaStream_t st);
 
-template <typename T, int POLY, bool PINGPONG, bool SPLIT>
+template <typename T, int POLY>
 static int launch_k(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const XattnParams& prm, dim3 grid,
                     cudaStream_t st) {
-    auto kern = xattn_fwd_kernel<T, POLY, PINGPONG, SPLIT>;
+    auto kern = xattn_fwd_kernel<T, POLY>;
     const int smem = XattnSmem::bytes + 1024;
     static bool configured = false;      // per instantiation; cudaFuncSetAttribute is not a stream operation
     if (!configured) {
@@ -471,19 +441,11 @@ static int launch_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensor
                     int flags, cudaStream_t st) {
     int poly = (flags >> 8) & 0xF;       // RD_XATTN_POLY(n): 0 = default, 1 = off, n >= 2 = every n-th pair
     if (poly == 0) poly = kDefaultPoly;
-    if (flags & RD_XATTN_PINGPONG) {
-        if (poly == 4) return launch_k<T, 4, true, true>(mq, mk, mv, prm, grid, st);
-        return launch_k<T, 0, true, true>(mq, mk, mv, prm, grid, st);
-    }
-    if (flags & RD_XATTN_SINGLE_ISSUER) return launch_k<T, 0, false, false>(mq, mk, mv, prm, grid, st);
     switch (poly) {
-        case 1: return launch_k<T, 0, false, true>(mq, mk, mv, prm, grid, st);
-        case 2: return launch_k<T, 2, false, true>(mq, mk, mv, prm, grid, st);
-        case 3: return launch_k<T, 3, false, true>(mq, mk, mv, prm, grid, st);
-        case 4: return launch_k<T, 4, false, true>(mq, mk, mv, prm, grid, st);
-        case 6: return launch_k<T, 6, false, true>(mq, mk, mv, prm, grid, st);
-        case 8: return launch_k<T, 8, false, true>(mq, mk, mv, prm, grid, st);
-        default: set_error("RD_XATTN_POLY(%d) is not instantiated (1, 2, 3, 4, 6, 8)", poly); return RD_ERR_UNSUPPORTED;
+        case 1: return launch_k<T, 0>(mq, mk, mv, prm, grid, st);
+        case 4: return launch_k<T, 4>(mq, mk, mv, prm, grid, st);
+        case 8: return launch_k<T, 8>(mq, mk, mv, prm, grid, st);
+        default: set_error("RD_XATTN_POLY(%d) is not instantiated (1, 4, 8)", poly); return RD_ERR_UNSUPPORTED;
     }
 }
 
@@ -518,7 +480,7 @@ extern "C" int rd_xattn_fwd(const void* q, const void* k, const void* v, void* o
     if (int e = make_qkv_map(&mv, v, dtype, B, H, Sk, v_sb, v_ss, v_sh, kBN)) return e;
     XattnParams prm{};
     prm.o = o; prm.o_sb = o_sb; prm.o_ss = o_ss; prm.o_sh = o_sh;
-    prm.Sq = Sq; prm.Sk = Sk; prm.n_kv_tiles = (Sk + kBN - 1) / kBN;
+    prm.Sq = Sq; prm.Sk = Sk; prm.n_kv_tiles = (Sk + kBN - 1) / kBN; prm.n_steps = (Sk + kBK - 1) / kBK;
     prm.scale_log2 = scale * 1.4426950408889634f;
     dim3 grid((Sq + kNQ * kBM - 1) / (kNQ * kBM), H, B);
     if (dtype == RD_F16) return launch_t<__half>(mq, mk, mv, prm, grid, flags, st);
