@@ -144,13 +144,33 @@ def bench_align(args):
     print(json.dumps(dict(bench="merge", case="150f 768x432 fp16", ms=med, GBs=mb / med / 1e6, frac_of_hbm=mb / med / 1e6 / hbm)))
 
 
+def bench_gn(args):
+    """Channels-last element-wise kernels on VAE-decoder-sized activations (12 frames of the fast preset)."""
+    from rollingdepth_b200 import ops
+    dev = torch.device("cuda:0")
+    hbm, _, src = peaks()
+    for name, N, H, W, Cc in [("dec L3 12x432x768x128", 12, 432, 768, 128), ("dec L2 12x216x384x256", 12, 216, 384, 256),
+                              ("dec L1 12x108x192x512", 12, 108, 192, 512)]:
+        x = torch.randn(N, Cc, H, W, device=dev, dtype=torch.float16).contiguous(memory_format=torch.channels_last)
+        res = torch.randn_like(x)
+        w = torch.ones(Cc, device=dev, dtype=torch.float16)
+        b = torch.zeros(Cc, device=dev, dtype=torch.float16)
+        nbytes = x.numel() * 2
+        med, best = time_cuda(lambda: ops.group_norm_nhwc(x, 32, w, b, 1e-6, True))
+        print(json.dumps(dict(bench="groupnorm+silu", case=name, ms=med, algorithmic_GB=3 * nbytes / 1e9,
+                              GBs=3 * nbytes / med / 1e6, frac_of_hbm=3 * nbytes / med / 1e6 / hbm, peak_src=src)), flush=True)
+        med, best = time_cuda(lambda: ops.bias_residual_nhwc(x, bias=b, residual=res, inplace=False))
+        print(json.dumps(dict(bench="bias+residual", case=name, ms=med, algorithmic_GB=3 * nbytes / 1e9,
+                              GBs=3 * nbytes / med / 1e6, frac_of_hbm=3 * nbytes / med / 1e6 / hbm, peak_src=src)), flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["attn", "align"])
+    ap.add_argument("what", choices=["attn", "align", "gn"])
     ap.add_argument("--full", action="store_true")
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--flags", type=int, nargs="+", default=[0])
     ap.add_argument("--only", default="")
     a = ap.parse_args()
-    (bench_attn if a.what == "attn" else bench_align)(a)
+    {"attn": bench_attn, "align": bench_align, "gn": bench_gn}[a.what](a)

@@ -13,6 +13,8 @@
 
 #if defined(XATTN_V5)
 #include "attn_variants/xattn_v5.cu"      // copy of attn_variants/xattn_v5_*.cu.txt made by the build line (A/B runs)
+#elif defined(XATTN_V6)
+#include "attn_variants/xattn_v6.cu"
 #elif defined(XATTN_V7)
 #include "attn_variants/xattn_v7.cu"      // build with -I rollingdepth_b200/csrc
 #else
@@ -72,12 +74,18 @@ int run(int B, int H, int S, int flags, int iters, rd_dtype dt) {
 #if defined(RD_XATTN_TRACE) && !defined(XATTN_V5)
     unsigned long long tr[16];
     cudaMemcpyFromSymbol(tr, rd::rd_xattn_trace, sizeof(tr));
-    const double tiles = (double)(tr[8] + tr[9]) * ((S + 63) / 64);   // steps x traced warps
+#if defined(XATTN_V6) || defined(XATTN_V7)
+    const int step_keys = 64;
     const char* names[8] = {"wait S_FULL", "LDTM + wait", "max + rescale", "exp + pack + STTM", "st wait + P_FULL", "-", "-", "-"};
+#else
+    const int step_keys = 128;
+    const char* names[8] = {"wait S_FULL", "LDTM S + S_FREE", "mask + row max", "wait O_READY", "rescale (lazy)", "exp + pack + STTM", "st wait + P_FULL", "-"};
+#endif
+    const double tiles = (double)(tr[8] + tr[9]) * ((S + step_keys - 1) / step_keys);   // steps x traced warps
     double tot = 0;
     for (int i = 0; i < 7; ++i) tot += tr[i] / tiles;
     for (int i = 0; i < 7; ++i) printf("  %-26s %8.1f cycles/step  (%4.1f%%)\n", names[i], tr[i] / tiles, 100.0 * tr[i] / tiles / tot);
-    printf("  total                      %8.1f cycles per 64-key step per softmax warp\n", tot);
+    printf("  total                      %8.1f cycles per %d-key step per softmax warp\n", tot, step_keys);
 #ifdef RD_XATTN_TIMELINE
     {
         static long long tl[4][32][8];
