@@ -231,6 +231,8 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms), out, L.LAUNCHES
 
+    if args.stage_times:
+        pipe.stage_events = []
     proc = next(iter(pipe.unet.attn_processors.values()))
     for _ in range(args.warmup):
         step(dev_frames)
@@ -285,6 +287,8 @@ def run_ours(args):
                     "d2h_bytes_per_step": d2h, "steps": k2},
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cb, "finite_output": finite,
         }
+        if args.stage_times:
+            line["stage_ms_last_step_rank0"] = {k: round(v, 1) for k, v in pipe.stage_times_ms()}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -304,6 +308,7 @@ if __name__ == "__main__":
     ap.add_argument("--fused-norm", type=int, default=1)
     ap.add_argument("--cudnn-benchmark", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stage-times", action="store_true", help="add per-stage device times of the last timed step (rank 0)")
     ap.add_argument("--frames", type=int, default=0,
                     help="profiling only: shorter clip than the preset (the ncu launch list); NOT a bench configuration")
     a = ap.parse_args()

@@ -59,6 +59,10 @@ class RollingDepthPipeline:
         self.timings: Dict[str, float] = {}
         self.channels_last, self.fused_norm = bool(channels_last), bool(fused_norm)
         self._tuned_for = None
+        self.output_mode = "fresh"      # or "pinned_views": see the output stage of forward()
+        self._staging: List[torch.Tensor] = []      # pinned device -> host staging buffers, reused by every call
+        self._stage_slot = 0
+        self._stage_events: Dict[int, torch.cuda.Event] = {}
         if install_processor:
             self.unet.set_attn_processor(B200XFrameAttnProcessor())
         logging.debug(f"Pipeline initialized: {type(self)}")
@@ -92,6 +96,20 @@ class RollingDepthPipeline:
                 if isinstance(sub, (GroupNormAct, BiasConv2d, ResnetBlock2D, Upsample2D)):
                     sub.fused = self.fused_norm and self.channels_last
         self._tuned_for = key
+
+    # ------------------------------------------------------------------ optional per-stage device timing
+    def _mark(self, name: str) -> None:
+        """Record a CUDA event at a stage boundary when `self.stage_events` is a list (bench.py --stage-times)."""
+        ev = getattr(self, "stage_events", None)
+        if ev is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            ev.append((name, e))
+
+    def stage_times_ms(self):
+        """[(stage, ms)] between consecutive marks of the last forward (call after a synchronize)."""
+        ev = getattr(self, "stage_events", None) or []
+        return [(ev[i + 1][0], ev[i][1].elapsed_time(ev[i + 1][1])) for i in range(len(ev) - 1)]
 
     def enable_sharding(self, group=None) -> "RollingDepthPipeline":
         """Shard snippets over the ranks of `group` (default: the world group)."""
@@ -211,8 +229,13 @@ class RollingDepthPipeline:
         # ----------------- Initial prediction -----------------
         # :263 converts on the host and then copies; copying first (async from pinned memory) and rounding to the
         # pipeline dtype on the device gives the same values (one round-to-nearest either way) without the CPU pass
+        if getattr(self, "stage_events", None) is not None:
+            self.stage_events = []
+        self._mark("start")
         input_frames = input_frames.to(device, non_blocking=True).to(self.dtype)
+        self._mark("h2d+cast")
         rgb_latent = self.encode_rgb(input_frames, max_batch_size=max_vae_bs, verbose=verbose, sharded=True)
+        self._mark("vae_encode(+gather)")
         if self.empty_text_embed is None:
             self.encode_empty_text()
         B, seq_len, _, h, w = rgb_latent.shape
@@ -244,6 +267,7 @@ class RollingDepthPipeline:
         self.last_alignment = (scales, translations, loss_history)
         # d -= d.min(); d /= d.max(); d = d*2-1, min/max come fused out of the merge kernel
         ops.renorm_(depth_coaligned, depth_aligner.merged_minmax)
+        self._mark("coalign(+exchange)+merge+renorm")
 
         # ----------------- Refinement (:322-345) -----------------
         if refine_step > 0:
@@ -259,23 +283,58 @@ class RollingDepthPipeline:
             depth_pred = depth_coaligned
 
         # ----------------- Output (:347-354): everything to the host -----------------
-        # asynchronous copies into pinned host tensors (torch's caching host allocator), one sync at the end
+        # The reference's `.cpu()` calls return fresh pageable tensors.  Page-locking ~1 GB of fresh host memory per call
+        # (torch.empty(pin_memory=True)) cost 0.65 s of a 5.8 s step, so the device -> host copies go asynchronously
+        # into pipeline-owned pinned staging buffers (allocated once, reused by every call) and, after ONE
+        # synchronisation, are copied on the host into fresh pageable tensors (reference semantics).
+        # `output_mode = "pinned_views"` skips that host copy and returns views of the staging buffers, valid until the
+        # next call of this pipeline object.
+        self._stage_slot = 0
+        self._stage_events = {}
         out = RollingDepthOutput(
             input_rgb=self._to_host(input_frames.squeeze(0) / 2.0 + 0.5),
             depth_pred=self._to_host(depth_pred.squeeze(0)),
             snippet_ls=[self._to_host(snippet) for snippet in snippet_pred_ls],
             depth_coaligned=self._to_host(depth_coaligned.squeeze(0)),
         )
+        self._mark("refine+outputs_d2h")
+        if self.output_mode != "pinned_views":
+            # host copies start as soon as the corresponding transfer has landed (per-tensor events)
+            out = RollingDepthOutput(
+                input_rgb=self._detach_host(out.input_rgb), depth_pred=self._detach_host(out.depth_pred),
+                snippet_ls=[self._detach_host(t) for t in out.snippet_ls],
+                depth_coaligned=self._detach_host(out.depth_coaligned))
         torch.cuda.current_stream(device).synchronize()
         return out
 
-    @staticmethod
-    def _to_host(t: torch.Tensor) -> torch.Tensor:
+    def _to_host(self, t: torch.Tensor) -> torch.Tensor:
+        """Asynchronous device -> host copy into the next pinned staging buffer of this pipeline."""
         if not t.is_cuda:
             return t
-        host = torch.empty(t.shape, dtype=t.dtype, device="cpu", pin_memory=True)
+        t = t.contiguous()
+        nbytes = t.numel() * t.element_size()
+        slot = self._stage_slot
+        self._stage_slot += 1
+        if slot >= len(self._staging):
+            self._staging.append(None)
+        buf = self._staging[slot]
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device="cpu", pin_memory=True)
+            self._staging[slot] = buf
+        host = buf[:nbytes].view(t.dtype).view(t.shape)
         host.copy_(t, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._stage_events[host.data_ptr()] = ev
         return host
+
+    def _detach_host(self, t: torch.Tensor) -> torch.Tensor:
+        """Fresh pageable copy of a staging view, taken once its transfer has completed."""
+        ev = self._stage_events.pop(t.data_ptr(), None)
+        if ev is None:
+            return t
+        ev.synchronize()
+        return torch.empty(t.shape, dtype=t.dtype, device="cpu").copy_(t)      # pageable, like the reference's .cpu()
 
     # ------------------------------------------------------------------ initial snippet inference (:356-463)
     def init_snippet_infer(self, rgb_latent, init_noise, dilations, cap_dilation, snippet_lengths, init_infer_steps,
@@ -301,12 +360,14 @@ class RollingDepthPipeline:
                     pred = self.single_step(rgb_snip, depth_snip, t, text)
                     depth_snip = self.scheduler.step(pred, t, depth_snip)
                 latents.append(depth_snip)
+            self._mark(f"unet+ddim d={dilation}")
             if latents:
                 depth_snippet_latent = torch.cat(latents, dim=0)  # [n_mine, n, 4, h, w]
                 decoded = self.decode_depth(depth_snippet_latent, max_batch_size=max_vae_bs, verbose=verbose)
             else:
                 H, W = self._decoded_hw(h, w)
                 decoded = torch.empty((0, snippet_len, 1, H, W), device=self.device, dtype=self.dtype)
+            self._mark(f"vae_decode d={dilation}")
             if unload_snippet:
                 decoded = decoded.cpu()
             snippet_pred_ls.append(decoded)
