@@ -213,6 +213,11 @@ int rd_bias_residual_nhwc(const void* x, const void* bias, const void* vec, cons
 int rd_upsample_nearest_nhwc(const void* x, void* y, int N, int Hi, int Wi, int Ho, int Wo, int C,
                              rd_dtype dtype, void* stream);
 
+/* GEGLU gate of the transformer feed-forward (diffusers/src/diffusers/models/activations.py GEGLU.forward, called from
+ * attention.py FeedForward): y[m, d] = proj[m, d] * gelu(proj[m, D + d]) for a contiguous [M, 2 D] projection; exact
+ * (erf) GELU, rounding as torch (gelu in fp32 -> dtype, product in fp32 -> dtype).  One pass instead of gelu + mul. */
+int rd_geglu(const void* proj, void* y, int64_t M, int D, rd_dtype dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -273,6 +273,30 @@ __global__ void __launch_bounds__(256) upsample_nearest_nhwc_kernel(const UpPara
     }
 }
 
+// GEGLU gate of the transformer feed-forward (diffusers/src/diffusers/models/activations.py GEGLU.forward):
+// proj [M, 2 D] -> out [M, D] = proj[:, :D] * gelu(proj[:, D:]); one pass instead of torch's gelu + mul over two
+// strided halves.  Rounding as torch: gelu in fp32 -> T, product in fp32 -> T.
+template <typename T>
+__global__ void __launch_bounds__(256) geglu_kernel(const T* __restrict__ x, T* __restrict__ y, long long M, int DV) {
+    constexpr int VN = GnVec<T>::N;
+    const long long total = M * DV;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long m = i / DV;
+        const int dv = (int)(i - m * DV);
+        const T* row = x + (size_t)m * (2 * DV * VN);
+        float h[VN], g[VN];
+        gn_unpack<T>(ldg_stream16(row + (size_t)dv * VN), h);
+        gn_unpack<T>(ldg_stream16(row + (size_t)(DV + dv) * VN), g);
+        alignas(16) T o[VN];
+#pragma unroll
+        for (int k = 0; k < VN; ++k) {
+            const float gel = Cvt<T>::round(g[k] * 0.5f * (1.0f + erff(g[k] * 0.70710678118654752440f)));
+            o[k] = Cvt<T>::from_f(h[k] * gel);
+        }
+        *reinterpret_cast<uint4*>(y + (size_t)i * VN) = *reinterpret_cast<const uint4*>(o);
+    }
+}
+
 static int gn_plan(GnParams& p, int es) {
     const int VN = 16 / es;
     // slice the channels over blockIdx.z until one pixel row of a slice fits one CTA (<= 512 vectors);
@@ -396,6 +420,26 @@ int rd_upsample_nearest_nhwc(const void* x, void* y, int N, int Hi, int Wi, int 
     const int blocks = (int)(want > (long long)num_sms() * 32 ? (long long)num_sms() * 32 : want);
     upsample_nearest_nhwc_kernel<uint4><<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
     RD_LAUNCH_CHECK("upsample_nearest_nhwc_kernel");
+    return RD_OK;
+}
+
+int rd_geglu(const void* proj, void* y, int64_t M, int D, rd_dtype dtype, void* stream) {
+    RD_CHECK_ARG(proj && y && M >= 1 && D >= 1, "bad argument");
+    RD_CHECK_ARG(dtype == RD_F32 || dtype == RD_F16 || dtype == RD_BF16, "bad dtype");
+    const int es = dtype == RD_F32 ? 4 : 2, VN = 16 / es;
+    if (D % VN != 0) { set_error("D=%d is not a multiple of the 16-byte vector width", D); return RD_ERR_UNSUPPORTED; }
+    RD_CHECK_ARG((((uintptr_t)proj | (uintptr_t)y) & 15) == 0, "pointers must be 16-byte aligned");
+    const int DV = D / VN;
+    const long long total = (long long)M * DV;
+    long long want = (total + 255) / 256;
+    const int blocks = (int)(want > (long long)num_sms() * 16 ? (long long)num_sms() * 16 : want);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case RD_F32: geglu_kernel<float><<<blocks, 256, 0, st>>>((const float*)proj, (float*)y, M, DV); break;
+        case RD_F16: geglu_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)proj, (__half*)y, M, DV); break;
+        default:     geglu_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)proj, (__nv_bfloat16*)y, M, DV); break;
+    }
+    RD_LAUNCH_CHECK("geglu_kernel");
     return RD_OK;
 }
 

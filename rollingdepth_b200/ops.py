@@ -161,3 +161,17 @@ def upsample_nearest_nhwc(x: torch.Tensor, size) -> torch.Tensor:
     L.check(code, "rd_upsample_nearest_nhwc")
     L.count_launches(1)
     return y
+
+
+def geglu(proj: torch.Tensor) -> torch.Tensor:
+    """proj[..., :D] * gelu(proj[..., D:]) for a contiguous [..., 2 D] projection (one fused pass)."""
+    L.require_cuda(proj)
+    if not proj.is_contiguous():
+        proj = proj.contiguous()
+    D = proj.shape[-1] // 2
+    M = proj.numel() // (2 * D)
+    y = torch.empty(*proj.shape[:-1], D, dtype=proj.dtype, device=proj.device)
+    code = L.lib().rd_geglu(L.ptr(proj), L.ptr(y), M, D, L.dtype_code(proj.dtype), L.stream_ptr(proj.device))
+    L.check(code, "rd_geglu")
+    L.count_launches(1)
+    return y

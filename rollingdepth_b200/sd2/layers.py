@@ -242,8 +242,14 @@ class GEGLU(nn.Module):
         super().__init__()
         self.proj = nn.Linear(dim_in, dim_out * 2)
 
+    fused = True        # one rd_geglu pass on CUDA instead of gelu + mul over the two strided halves
+
     def forward(self, x):
-        h, gate = self.proj(x).chunk(2, dim=-1)
+        proj = self.proj(x)
+        if self.fused and proj.is_cuda and proj.shape[-1] % 16 == 0:
+            from .. import ops
+            return ops.geglu(proj)
+        h, gate = proj.chunk(2, dim=-1)
         return h * F.gelu(gate)
 
 

@@ -461,3 +461,24 @@ def test_bias_residual_and_upsample_nhwc(dtype):
     for size in ((26, 34), (27, 33), (14, 24)):
         up = ops.upsample_nearest_nhwc(x, size)
         assert torch.equal(up, torch.nn.functional.interpolate(x, size=size, mode="nearest"))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+def test_geglu_matches_torch(dtype):
+    """rd_geglu vs the reference's two-op form (activations.py GEGLU.forward) evaluated by torch on the same device."""
+    from rollingdepth_b200 import ops
+    dev = _dev()
+    g = torch.Generator().manual_seed(3)
+    for shape in [(3, 77, 2 * 1280), (2, 5, 2 * 64), (1, 1000, 2 * 320)]:
+        proj = (torch.randn(shape, generator=g) * 2.0).to(dev, dtype)
+        h, gate = proj.chunk(2, dim=-1)
+        ref = h * torch.nn.functional.gelu(gate)
+        out = ops.geglu(proj)
+        assert out.shape == ref.shape and out.dtype == ref.dtype
+        if dtype == torch.float32:
+            torch.testing.assert_close(out, ref, rtol=2e-6, atol=2e-6)
+        else:
+            # same operation order and roundings as torch: at most one ulp from erff differences
+            ulp = 2.0 ** (-10 if dtype == torch.float16 else -7)
+            assert float(((out.float() - ref.float()).abs() / ref.float().abs().clamp_min(1e-3)).max()) <= 2 * ulp
