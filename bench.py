@@ -302,8 +302,8 @@ if __name__ == "__main__":
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--preset", default="fast", choices=list(PRESETS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--snippet-batch", type=int, default=8)
-    ap.add_argument("--max-vae-bs", type=int, default=12)
+    ap.add_argument("--snippet-batch", type=int, default=16)
+    ap.add_argument("--max-vae-bs", type=int, default=36)
     ap.add_argument("--channels-last", type=int, default=1)
     ap.add_argument("--fused-norm", type=int, default=1)
     ap.add_argument("--cudnn-benchmark", type=int, default=1)

@@ -46,7 +46,7 @@ class RollingDepthPipeline:
     depth_latent_scale_factor = 0.18215
     N_CHANNEL_PER_LATENT = 4
 
-    def __init__(self, unet, vae, scheduler, text_encoder=None, tokenizer=None, snippet_batch: int = 8,
+    def __init__(self, unet, vae, scheduler, text_encoder=None, tokenizer=None, snippet_batch: int = 16,
                  install_processor: bool = True, channels_last: bool = True, fused_norm: bool = True):
         self.unet = unet
         self.vae = vae

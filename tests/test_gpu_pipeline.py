@@ -89,3 +89,28 @@ def test_pipeline_fp16_matches_oracle_on_device():
         assert float((a.float() - b.float().cpu()).abs().max()) < 2e-2
     assert _absrel(res.depth_pred, ora.depth_pred.cpu()) <= 3e-3   # fp16 noise floor of the tiny random model
     assert torch.isfinite(res.depth_pred.float()).all()
+
+
+def test_output_modes_agree_and_results_are_fresh_by_default(golden_dir):
+    """Default outputs are fresh pageable CPU tensors (the reference's `.cpu()` semantics) that survive the next call;
+    `output_mode = "pinned_views"` returns the same values as views of the pipeline's staging buffers."""
+    from rollingdepth_b200.pipeline import RollingDepthPipeline
+    from rollingdepth_b200.scheduler import DDIMSchedule
+    dev = _dev()
+    g = np.load(os.path.join(golden_dir, "models_pipeline.npz"))
+    unet, vae = _tiny(dev, torch.float32)
+    pipe = RollingDepthPipeline(unet, vae, DDIMSchedule(**mu.DDIM_CFG), snippet_batch=4)
+    pipe.empty_text_embed = torch.from_numpy(g["pipe_text"]).to(dev)
+    frames = torch.from_numpy(g["pipe_frames"])
+    a = _run(pipe, frames, [1, 3], 0, torch.Generator().manual_seed(0))
+    keep = a.depth_pred.clone()
+    assert not a.depth_pred.is_pinned() and not a.snippet_ls[0].is_pinned()
+    b = _run(pipe, frames.flip(1), [1, 3], 0, torch.Generator().manual_seed(0))     # different input, same buffers
+    assert torch.equal(a.depth_pred, keep), "results of an earlier call were overwritten"
+    assert not torch.equal(a.depth_pred, b.depth_pred)
+    pipe.output_mode = "pinned_views"
+    c = _run(pipe, frames, [1, 3], 0, torch.Generator().manual_seed(0))
+    assert c.depth_pred.is_pinned()
+    assert torch.equal(c.depth_pred, a.depth_pred) and torch.equal(c.depth_coaligned, a.depth_coaligned)
+    for x, y in zip(c.snippet_ls, a.snippet_ls):
+        assert torch.equal(x, y)

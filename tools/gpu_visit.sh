@@ -17,10 +17,11 @@ timeout 600 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/b
 kill $SMI
 timeout 600 python tools/microbench.py attn > gpurun_out/mb_attn_$T.log 2>&1; tail -8 gpurun_out/mb_attn_$T.log
 timeout 600 python tools/microbench.py align --iters 200 > gpurun_out/mb_align_$T.log 2>&1; tail -6 gpurun_out/mb_align_$T.log
+timeout 300 python tools/microbench.py gn > gpurun_out/mb_gn_$T.log 2>&1; tail -6 gpurun_out/mb_gn_$T.log
 if [ "${RD_SKIP_NCU:-0}" != "1" ]; then
-CMD="python bench.py --frames 30 --steps 1 --warmup 1 --no-cpu-baseline"
+CMD="python bench.py --frames 12 --steps 1 --warmup 0 --no-cpu-baseline"
 timeout 600 $CMD > gpurun_out/plain_$T.log 2>&1 &&
-timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 60000 --csv --log-file gpurun_out/launches_$T.csv $CMD > gpurun_out/ncu_launches_$T.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv --log-file gpurun_out/launches_$T.csv $CMD > gpurun_out/ncu_launches_$T.log 2>&1
 echo "launch list exit=$?"; wc -l gpurun_out/launches_$T.csv
 CMD2=(python tools/microbench.py attn --only "full L0")
 timeout 300 "${CMD2[@]}" > gpurun_out/plain2_$T.log 2>&1 &&
