@@ -76,24 +76,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
-// Relaxed variants for waits whose payload travels through TMEM (ordered by tcgen05.fence::after_thread_sync, not by the
-// mbarrier's acquire): A/B switch RD_MBAR_RELAXED of the attention kernel's softmax warps.
-__device__ __forceinline__ bool mbar_test_wait_relaxed(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.test_wait.parity.relaxed.cta.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
-    if (mbar_test_wait_relaxed(bar, parity)) return;
-    mbar_wait(bar, parity);
-}
-
 // ---------------------------------------------------------------- fences
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

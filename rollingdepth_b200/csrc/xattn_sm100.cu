@@ -300,13 +300,8 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         RD_TRACE_DECL
         if (PINGPONG && t == 1) named_bar_arrive(1, kSoftmaxThreads);   // warpgroup 0 goes first
 
-#ifdef RD_MBAR_RELAXED
-#define SM_WAIT mbar_wait_relaxed
-#else
-#define SM_WAIT mbar_wait
-#endif
         for (int j = 0; j < n_tiles; ++j) {
-            SM_WAIT(s_full, j & 1);
+            mbar_wait(s_full, j & 1);
             tc_fence_after();
             RD_TRACE(0)
             uint32_t sr[4][32];
@@ -344,7 +339,7 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             if (PINGPONG) named_bar_sync(1 + t, kSoftmaxThreads);      // our turn on the MUFU pipe
             if (j > 0) {
                 // P (and O) may only be touched once PV(j-1) has completed
-                SM_WAIT(o_ready, (j - 1) & 1);
+                mbar_wait(o_ready, (j - 1) & 1);
                 tc_fence_after();
                 RD_TRACE(3)
                 const bool need = (m_new - m_used) * sl2 > kRescaleThreshold;
