@@ -54,8 +54,13 @@ def test_snippet_sharding_two_gpus_matches_single_gpu(tmp_path):
     script = tmp_path / "worker.py"
     script.write_text(_WORKER)
     env = dict(os.environ, RD_ROOT=ROOT)
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
-                       capture_output=True, text=True, env=env, timeout=900)
+    # one retry on another port: a rendezvous / NCCL bring-up hiccup on a fresh box is not a parity failure
+    # (the numerical assertions live in the worker and would fail identically both times)
+    for port in ("29541", "29547"):
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                            "--master-addr", "127.0.0.1", "--master-port", port, str(script)],
+                           capture_output=True, text=True, env=env, timeout=900)
+        if r.returncode == 0 or "AssertionError" in r.stdout + r.stderr:
+            break
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count(" ok") == 2
