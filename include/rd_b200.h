@@ -62,6 +62,9 @@ int rd_device_arch(void);
 /* share of the softmax exponentials evaluated by a degree-3 polynomial on the FMA pipes instead of MUFU.EX2
  * (the MUFU pipe is the first ceiling at head_dim 64): every n-th score pair; n = 1 disables, 0 = tuned default */
 #define RD_XATTN_POLY(n) (((n) & 0xF) << 8)
+/* query tiles per CTA: 0 = chosen by grid size (three 128-row tiles on many-wave grids of long sequences, else two),
+ * 2 / 3 = force (A/B measurements; the parity tests run both) */
+#define RD_XATTN_TILES(n) (((n) & 3) << 4)
 int rd_xattn_fwd(const void* q, const void* k, const void* v, void* o,
                  int B, int H, int Sq, int Sk, int D,
                  int64_t q_sb, int64_t q_ss, int64_t q_sh,

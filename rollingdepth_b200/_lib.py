@@ -18,6 +18,10 @@ RD_F32, RD_F16, RD_BF16 = 0, 1, 2
 RD_MAX_GROUPS, RD_MAX_WINDOW = 8, 8
 
 
+def XATTN_TILES(n: int) -> int:
+    return (n & 3) << 4
+
+
 def XATTN_POLY(n: int) -> int:
     return (n & 0xF) << 8
 

@@ -75,7 +75,7 @@ XATTN_SHAPES = [
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("shape", XATTN_SHAPES)
-@pytest.mark.parametrize("flags", [0, 2, 4 << 8])
+@pytest.mark.parametrize("flags", [0, 2, 4 << 8, 2 << 4, 3 << 4, (3 << 4) | (4 << 8)])
 def test_xattn_tcgen05_matches_oracle(shape, dtype, flags):
     from rollingdepth_b200 import ops
     dev = _dev()

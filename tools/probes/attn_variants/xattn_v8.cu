@@ -5,8 +5,9 @@
 // At head_dim 64 one 128x128 score tile costs 512 tensor-pipe cycles (QK^T + PV) but 1024 MUFU cycles
 // (16 exponentials / clk / SM), so the kernel is organised around keeping the MUFU pipe busy:
 //
-// One CTA per SM = TWO 128-row query tiles of one (batch, head) that share every K/V tile.  Warp roles (384 threads;
-// setmaxnreg moves registers from the third warpgroup to the softmax warpgroups: 88 vs 208 per thread):
+// VARIANT v8: THREE 128-row query tiles per CTA, 64-key steps (S 64 + O 64 + P 32 TMEM columns per tile), three softmax
+// warps per SM sub-partition, one issuer warp per tile, 512 threads x 128 registers (no setmaxnreg).
+// One CTA per SM = query tiles of one (batch, head) that share every K/V tile.  Warp roles:
 //   warps 0-3  softmax of query tile 0, warps 4-7 softmax of query tile 1.  Each thread owns one query row
 //              (= one TMEM lane): S -> registers (tcgen05.ld), row maximum, lazy (thresholded) rescaling of O
 //              in TMEM, exponentials, P -> TMEM as packed fp16/bf16 (tcgen05.st), epilogue O / l -> global.
@@ -51,16 +52,18 @@ __device__ unsigned long long rd_xattn_trace[16];
 #endif
 
 constexpr int kBM = 128;       // rows per query tile
-constexpr int kNQ = 2;         // query tiles per CTA
-constexpr int kBN = 128;       // keys per K/V tile
+constexpr int kNQ = 3;         // query tiles per CTA
+constexpr int kBN = 128;       // keys per K/V tile (one TMA box)
+constexpr int kBK = 64;        // keys per softmax / MMA step
+constexpr int kStepBytes = kBK * 64 * 2;
 constexpr int kD = 64;         // head dim
 constexpr int kStages = 3;
 constexpr int kTileBytes = kBN * kD * 2;   // 16384
 constexpr int kSoftmaxThreads = kNQ * 128;
 constexpr int kThreads = kSoftmaxThreads + 128;   // third warpgroup: two MMA warps, TMA warp, one idle warp (register donors)
-constexpr int kMmaWarp = kNQ * 4, kTmaWarp = kNQ * 4 + 2;
+constexpr int kMmaWarp = kNQ * 4, kTmaWarp = kNQ * 4 + 3;
 constexpr uint32_t kTmemCols = 512;
-constexpr uint32_t kColS = 0, kColO = 256, kColP = 384;   // + 128 t, + 64 t, + 64 t
+constexpr uint32_t kColTile = 160, kColS = 0, kColO = 64, kColP = 128;   // per tile: S 64, O 64, P 32 columns
 constexpr float kRescaleThreshold = 8.0f;  // log2 units; p stays <= 2^8
 
 struct XattnSmem {
@@ -80,7 +83,7 @@ static_assert(O_READY + kNQ <= 32, "barrier table too small");
 struct XattnParams {
     void* o;
     long long o_sb, o_ss, o_sh;
-    int Sq, Sk, n_kv_tiles;
+    int Sq, Sk, n_kv_tiles, n_steps;
     float scale_log2;   // scale * log2(e)
 };
 
@@ -161,6 +164,28 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
+// row maximum of one 64-key step: 8 independent chains of 3-input max (one dependent chain would be ~250 cycles)
+__device__ __forceinline__ float row_max64(const uint32_t (&a)[32], const uint32_t (&b)[32]) {
+    float mx[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) mx[q] = max3(__uint_as_float(a[4 * q]), __uint_as_float(a[4 * q + 1]), __uint_as_float(a[4 * q + 2]));
+#pragma unroll
+    for (int q = 0; q < 8; ++q) mx[q] = max3(mx[q], __uint_as_float(a[4 * q + 3]), __uint_as_float(b[4 * q]));
+#pragma unroll
+    for (int q = 0; q < 8; ++q) mx[q] = max3(mx[q], __uint_as_float(b[4 * q + 1]), __uint_as_float(b[4 * q + 2]));
+#pragma unroll
+    for (int q = 0; q < 8; ++q) mx[q] = fmaxf(mx[q], __uint_as_float(b[4 * q + 3]));
+    return fmaxf(max3(mx[0], mx[1], mx[2]), max3(max3(mx[3], mx[4], mx[5]), mx[6], mx[7]));
+}
+
+__device__ __forceinline__ void mask_tail64(uint32_t (&a)[32], uint32_t (&b)[32], int valid) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        if (i >= valid) a[i] = 0xff800000u;        // -inf
+        if (32 + i >= valid) b[i] = 0xff800000u;
+    }
+}
+
 // POLY: every POLY-th score pair takes the polynomial exp2 path (0 = all on MUFU)
 // PINGPONG: the two softmax warpgroups alternate their exponential phases (named barriers 1 and 2)
 // SPLIT: one MMA issuer warp per query tile (false: a single in-order issuer for both tiles)
@@ -176,15 +201,15 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for the compiler
     const int lane = threadIdx.x & 31;
     const int q_blk = blockIdx.x, head = blockIdx.y, batch = blockIdx.z;
-    const int n_tiles = prm.n_kv_tiles;
+    const int n_tiles = prm.n_kv_tiles, n_steps = prm.n_steps;
 
     if (threadIdx.x == 0) {
         mbar_init(&bars[Q_FULL], 1);
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&bars[K_FULL + s], 1);
-            mbar_init(&bars[K_EMPTY + s], SPLIT ? kNQ : 1);    // one tcgen05.commit per issuer
+            mbar_init(&bars[K_EMPTY + s], kNQ);    // one tcgen05.commit per issuer
             mbar_init(&bars[V_FULL + s], 1);
-            mbar_init(&bars[V_EMPTY + s], SPLIT ? kNQ : 1);
+            mbar_init(&bars[V_EMPTY + s], kNQ);
         }
         for (int t = 0; t < kNQ; ++t) {
             mbar_init(&bars[S_FULL + t], 1);
@@ -210,7 +235,6 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
     // (setmaxnreg must dominate the code it applies to: one per role branch, no re-convergence in between)
     if (warp >= kMmaWarp) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
         if (warp == kTmaWarp) {
         // ===================================================== TMA producer
         if (lane == 0) {
@@ -228,67 +252,60 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 tma_load_4d(smem + XattnSmem::v + st * kTileBytes, &tm_v, &bars[V_FULL + st], 0, j * kBN, head, batch);
             }
         }
-        } else if (warp == kMmaWarp || (SPLIT && warp == kMmaWarp + 1)) {
-        // ===================================================== MMA issuer(s): query tiles [t_lo, t_hi)
-        // All 32 lanes run the loop (uniform control flow, descriptors in uniform registers); one elected lane issues.
+        } else if (warp < kMmaWarp + kNQ) {
+        // ===================================================== MMA issuer of query tile t (uniform control flow)
         {
             const bool leader = elect_one();
             constexpr uint32_t fmt = std::is_same<T, __nv_bfloat16>::value ? 1u : 0u;
-            constexpr uint32_t idesc_qk = make_idesc_f16(fmt, 0, 0, kBM, kBN);
+            constexpr uint32_t idesc_qk = make_idesc_f16(fmt, 0, 0, kBM, kBK);
             constexpr uint32_t idesc_pv = make_idesc_f16(fmt, 0, 1, kBM, kD);   // B = V is MN-major
-            const int t_lo = SPLIT ? warp - kMmaWarp : 0, t_hi = SPLIT ? t_lo + 1 : kNQ;
-            const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const int t = warp - kMmaWarp;
+            const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0) + t * kColTile;
+            const uint64_t dq = make_smem_desc_sw128(smem_u32(smem + XattnSmem::q + t * kTileBytes), 16, 1024);
 
-            auto issue_qk = [&](int j) {
-                const int st = j % kStages;
-                mbar_wait(&bars[K_FULL + st], (j / kStages) & 1);
-                const uint64_t dk = make_smem_desc_sw128(smem_u32(smem + XattnSmem::k + st * kTileBytes), 16, 1024);
-                for (int t = t_lo; t < t_hi; ++t) {
-                    if (j > 0) mbar_wait(&bars[S_FREE + t], (j - 1) & 1);   // softmax_t(j-1) has S in registers
-                    tc_fence_after();
-                    const uint64_t dq = make_smem_desc_sw128(smem_u32(smem + XattnSmem::q + t * kTileBytes), 16, 1024);
-                    if (leader) {
+            auto issue_qk = [&](int i) {
+                const int tile = i >> 1, st = tile % kStages, b = i & 1;
+                mbar_wait(&bars[K_FULL + st], (tile / kStages) & 1);
+                if (i > 0) mbar_wait(&bars[S_FREE + t], (i - 1) & 1);   // softmax_t(i-1) has S in registers
+                tc_fence_after();
+                const uint64_t dk = make_smem_desc_sw128(smem_u32(smem + XattnSmem::k + st * kTileBytes + b * kStepBytes), 16, 1024);
+                if (leader) {
 #pragma unroll
-                        for (int kk = 0; kk < kD / 16; ++kk)             // +32 bytes along K inside the 128B swizzle row
-                            mma_f16_ss(tm + kColS + t * 128, dq + 2 * kk, dk + 2 * kk, idesc_qk, kk > 0);
-                        if (t == t_hi - 1) mma_commit(&bars[K_EMPTY + st]);
-                        mma_commit(&bars[S_FULL + t]);
-                    }
-                    __syncwarp();
+                    for (int kk = 0; kk < kD / 16; ++kk)             // +32 bytes along K inside the 128B swizzle row
+                        mma_f16_ss(tm + kColS, dq + 2 * kk, dk + 2 * kk, idesc_qk, kk > 0);
+                    if (b == 1 || i == n_steps - 1) mma_commit(&bars[K_EMPTY + st]);
+                    mma_commit(&bars[S_FULL + t]);
                 }
+                __syncwarp();
             };
 
             mbar_wait(&bars[Q_FULL], 0);
             issue_qk(0);
-            for (int j = 0; j < n_tiles; ++j) {
-                if (j + 1 < n_tiles) issue_qk(j + 1);
-                const int st = j % kStages;
-                mbar_wait(&bars[V_FULL + st], (j / kStages) & 1);
-                const uint64_t dv = make_smem_desc_sw128(smem_u32(smem + XattnSmem::v + st * kTileBytes), 16, 1024);
-                for (int t = t_lo; t < t_hi; ++t) {
-                    mbar_wait(&bars[P_FULL + t], j & 1);
-                    tc_fence_after();
-                    if (leader) {
+            for (int j = 0; j < n_steps; ++j) {
+                if (j + 1 < n_steps) issue_qk(j + 1);
+                const int tile = j >> 1, st = tile % kStages, b = j & 1;
+                mbar_wait(&bars[V_FULL + st], (tile / kStages) & 1);
+                mbar_wait(&bars[P_FULL + t], j & 1);
+                tc_fence_after();
+                const uint64_t dv = make_smem_desc_sw128(smem_u32(smem + XattnSmem::v + st * kTileBytes + b * kStepBytes), 16, 1024);
+                if (leader) {
 #pragma unroll
-                        for (int kk = 0; kk < kBN / 16; ++kk)            // V advances 16 key rows = 2048 bytes per K step
-                            mma_f16_ts(tm + kColO + t * 64, tm + kColP + t * 64 + 8 * kk, dv + (uint64_t)(128 * kk),
-                                       idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
-                        if (t == t_hi - 1) mma_commit(&bars[V_EMPTY + st]);
-                        mma_commit(&bars[O_READY + t]);
-                    }
-                    __syncwarp();
+                    for (int kk = 0; kk < kBK / 16; ++kk)            // V advances 16 key rows = 2048 bytes per K step
+                        mma_f16_ts(tm + kColO, tm + kColP + 8 * kk, dv + (uint64_t)(128 * kk), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+                    if (b == 1 || j == n_steps - 1) mma_commit(&bars[V_EMPTY + st]);
+                    mma_commit(&bars[O_READY + t]);
                 }
+                __syncwarp();
             }
         }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
         // ===================================================== softmax warps (one query row per thread)
         const int t = warp >> 2;                       // query tile of this warpgroup
         const int row = (warp & 3) * 32 + lane;        // row inside the tile = TMEM lane
         const uint32_t lane_off = (uint32_t)((warp & 3) * 32) << 16;
-        const uint32_t tS = tmem_base + lane_off + kColS + t * 128, tO = tmem_base + lane_off + kColO + t * 64,
-                       tP = tmem_base + lane_off + kColP + t * 64;
+        const uint32_t tS = tmem_base + lane_off + t * kColTile + kColS, tO = tmem_base + lane_off + t * kColTile + kColO,
+                       tP = tmem_base + lane_off + t * kColTile + kColP;
         uint64_t* s_full = &bars[S_FULL + t];
         uint64_t* s_free = &bars[S_FREE + t];
         uint64_t* p_full = &bars[P_FULL + t];
@@ -298,45 +315,23 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         float m_used = -INFINITY;   // raw-score units
         float l = 0.f;
         RD_TRACE_DECL
-        if (PINGPONG && t == 1) named_bar_arrive(1, kSoftmaxThreads);   // warpgroup 0 goes first
 
-        for (int j = 0; j < n_tiles; ++j) {
+        for (int j = 0; j < n_steps; ++j) {
             mbar_wait(s_full, j & 1);
             tc_fence_after();
             RD_TRACE(0)
-            uint32_t sr[4][32];
-            tmem_ld32(tS + 0, sr[0]);
-            tmem_ld32(tS + 32, sr[1]);
-            tmem_ld32(tS + 64, sr[2]);
-            tmem_ld32(tS + 96, sr[3]);
+            uint32_t sa[32], sb[32];
+            tmem_ld32(tS + 0, sa);
+            tmem_ld32(tS + 32, sb);
             tmem_ld_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(s_free);
             RD_TRACE(1)
-
-            const int valid = prm.Sk - j * kBN;   // keys of this tile that exist
-            if (valid < kBN) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c * 32 + i >= valid) sr[c][i] = 0xff800000u;   // -inf
-            }
-            // row maximum: 8 independent chains of 3-input max (a single dependent chain of 128 FMNMX is ~500 cycles)
-            float mx[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) mx[q] = -INFINITY;
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-                for (int i = 0; i < 32; i += 2)
-                    mx[(i >> 1) & 7] = max3(mx[(i >> 1) & 7], __uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1]));
-            const float mt = fmaxf(max3(mx[0], mx[1], mx[2]), max3(max3(mx[3], mx[4], mx[5]), mx[6], mx[7]));
-            const float m_new = fmaxf(m_used, mt);
+            const int valid = prm.Sk - j * kBK;   // keys of this step that exist
+            if (valid < kBK) mask_tail64(sa, sb, valid);
+            const float m_new = fmaxf(m_used, row_max64(sa, sb));
             RD_TRACE(2)
-
-            if (PINGPONG) named_bar_sync(1 + t, kSoftmaxThreads);      // our turn on the MUFU pipe
             if (j > 0) {
                 // P (and O) may only be touched once PV(j-1) has completed
                 mbar_wait(o_ready, (j - 1) & 1);
@@ -362,33 +357,29 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
                 m_used = m_new;
             }
             RD_TRACE(4)
-
             const float mb = m_used * sl2;
             const uint64_t nmb2 = pack2(-mb, -mb);
-            uint64_t ls2[2] = {0ull, 0ull};            // independent partial row sums (two fp32 each)
+            uint64_t ls2[2] = {0ull, 0ull};
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t pk[32];
+            for (int h = 0; h < 2; ++h) {
+                uint32_t pk[16];
 #pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    const int c = half * 2 + cc;
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const uint64_t x2 = ffma2(pack2(__uint_as_float(sr[c][i]), __uint_as_float(sr[c][i + 1])), sl2_2, nmb2);
-                        float p0, p1;
-                        if (POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == POLY - 1) {
-                            ex2_poly2(x2, p0, p1);
-                        } else {
-                            float x0, x1;
-                            unpack2(x2, x0, x1);
-                            p0 = ex2(x0);
-                            p1 = ex2(x1);
-                        }
-                        ls2[(i >> 1) & 1] = fadd2(ls2[(i >> 1) & 1], pack2(p0, p1));
-                        pk[cc * 16 + (i >> 1)] = PackPair<T>::pack(p0, p1);
+                for (int i = 0; i < 32; i += 2) {
+                    const uint32_t r0 = h == 0 ? sa[i] : sb[i], r1 = h == 0 ? sa[i + 1] : sb[i + 1];
+                    const uint64_t x2 = ffma2(pack2(__uint_as_float(r0), __uint_as_float(r1)), sl2_2, nmb2);
+                    float p0, p1;
+                    if (POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == POLY - 1) {
+                        ex2_poly2(x2, p0, p1);
+                    } else {
+                        float x0, x1;
+                        unpack2(x2, x0, x1);
+                        p0 = ex2(x0);
+                        p1 = ex2(x1);
                     }
+                    ls2[(i >> 1) & 1] = fadd2(ls2[(i >> 1) & 1], pack2(p0, p1));
+                    pk[i >> 1] = PackPair<T>::pack(p0, p1);
                 }
-                tmem_st32(tP + half * 32, pk);
+                tmem_st16(tP + h * 16, pk);
             }
             {
                 float a0, a1, b0, b1;
@@ -401,13 +392,12 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(p_full);
-            if (PINGPONG && !(t == 1 && j == n_tiles - 1)) named_bar_arrive(1 + (t ^ 1), kSoftmaxThreads);
             RD_TRACE(6)
         }
         RD_TRACE_FLUSH
 
         // ------------------------------------------------- epilogue: O / l -> global
-        mbar_wait(o_ready, (n_tiles - 1) & 1);
+        mbar_wait(o_ready, (n_steps - 1) & 1);
         tc_fence_after();
         uint32_t orr[2][32];
         tmem_ld32(tO + 0, orr[0]);
@@ -445,12 +435,6 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 // ---------------------------------------------------------------------------------------------
 // host side (tensor maps: tensormap.cuh)
 // ---------------------------------------------------------------------------------------------
-// three-query-tile kernel (xattn_sm100_q3.cu)
-int xattn_q3_fwd(const void* q, const void* k, const void* v, void* o, int B, int H, int Sq, int Sk,
-                 int64_t q_sb, int64_t q_ss, int64_t q_sh, int64_t k_sb, int64_t k_ss, int64_t k_sh,
-                 int64_t v_sb, int64_t v_ss, int64_t v_sh, int64_t o_sb, int64_t o_ss, int64_t o_sh,
-                 rd_dtype dtype, float scale, int flags, cudaStream_t st);
-
 int xattn_f32_launch(const float* q, const float* k, const float* v, float* o, int B, int H, int Sq, int Sk,
                      const int64_t* qs, const int64_t* ks, const int64_t* vs, const int64_t* os, float scale,
                      cudaStream_t st);
@@ -518,23 +502,13 @@ extern "C" int rd_xattn_fwd(const void* q, const void* k, const void* v, void* o
     for (int i = 0; i < 12; ++i) RD_CHECK_ARG(all[i] >= 0 && (all[i] % 8) == 0, "stride %d (=%lld) must be a non-negative multiple of 8 elements", i, (long long)all[i]);
     RD_CHECK_ARG(((uintptr_t)q % 16) == 0 && ((uintptr_t)k % 16) == 0 && ((uintptr_t)v % 16) == 0 && ((uintptr_t)o % 16) == 0,
                  "q/k/v/o must be 16-byte aligned");
-    {   // kernel choice: three query tiles per CTA (384 rows) pay off on many-wave grids of long sequences; two tiles
-        // (256 rows) quantise better on small grids.  RD_XATTN_TILES(2 / 3) forces one (A/B, parity tests of both).
-        const int tiles = (flags >> 4) & 3;
-        const long long ctas3 = (long long)((Sq + 383) / 384) * H * B;
-        const bool big = ctas3 >= 4ll * num_sms() && Sk >= 2048;
-        const int poly = (flags >> 8) & 0xF;
-        if ((tiles == 3 || (tiles == 0 && big)) && !(flags & 3) && (poly == 0 || poly == 1 || poly == 4 || poly == 8))
-            return xattn_q3_fwd(q, k, v, o, B, H, Sq, Sk, q_sb, q_ss, q_sh, k_sb, k_ss, k_sh, v_sb, v_ss, v_sh, o_sb, o_ss, o_sh,
-                                dtype, scale, flags, st);
-    }
     CUtensorMap mq, mk, mv;
     if (int e = make_qkv_map(&mq, q, dtype, B, H, Sq, q_sb, q_ss, q_sh, kBM)) return e;
     if (int e = make_qkv_map(&mk, k, dtype, B, H, Sk, k_sb, k_ss, k_sh, kBN)) return e;
     if (int e = make_qkv_map(&mv, v, dtype, B, H, Sk, v_sb, v_ss, v_sh, kBN)) return e;
     XattnParams prm{};
     prm.o = o; prm.o_sb = o_sb; prm.o_ss = o_ss; prm.o_sh = o_sh;
-    prm.Sq = Sq; prm.Sk = Sk; prm.n_kv_tiles = (Sk + kBN - 1) / kBN;
+    prm.Sq = Sq; prm.Sk = Sk; prm.n_kv_tiles = (Sk + kBN - 1) / kBN; prm.n_steps = (Sk + kBK - 1) / kBK;
     prm.scale_log2 = scale * 1.4426950408889634f;
     dim3 grid((Sq + kNQ * kBM - 1) / (kNQ * kBM), H, B);
     if (dtype == RD_F16) return launch_t<__half>(mq, mk, mv, prm, grid, flags, st);

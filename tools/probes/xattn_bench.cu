@@ -3,7 +3,8 @@
 // softmax(QK^T)V, and (with -DRD_XATTN_TRACE) prints the per-phase cycle budget of the softmax warps.
 //
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 --expt-relaxed-constexpr -lineinfo [-DRD_XATTN_TRACE] \
-//        -I include tools/probes/xattn_bench.cu rollingdepth_b200/csrc/rd_abi.cu rollingdepth_b200/csrc/xattn_f32.cu \
+//        -I include -I rollingdepth_b200/csrc tools/probes/xattn_bench.cu rollingdepth_b200/csrc/rd_abi.cu \
+//        rollingdepth_b200/csrc/xattn_f32.cu rollingdepth_b200/csrc/xattn_sm100_q3.cu \
 //        -o tools/probes/bin/xattn_bench
 //   xattn_bench [B H S [flags [iters [bf16]]]]
 #include <cmath>
@@ -15,6 +16,8 @@
 #include "attn_variants/xattn_v5.cu"      // copy of attn_variants/xattn_v5_*.cu.txt made by the build line (A/B runs)
 #elif defined(XATTN_V6)
 #include "attn_variants/xattn_v6.cu"
+#elif defined(XATTN_V8)
+#include "attn_variants/xattn_v8.cu"
 #elif defined(XATTN_V7)
 #include "attn_variants/xattn_v7.cu"      // build with -I rollingdepth_b200/csrc
 #else
@@ -74,14 +77,17 @@ int run(int B, int H, int S, int flags, int iters, rd_dtype dt) {
 #if defined(RD_XATTN_TRACE) && !defined(XATTN_V5)
     unsigned long long tr[16];
     cudaMemcpyFromSymbol(tr, rd::rd_xattn_trace, sizeof(tr));
-#if defined(XATTN_V6) || defined(XATTN_V7)
+#if defined(XATTN_V8)
+    const int step_keys = 64;
+    const char* names[8] = {"wait S_FULL", "LDTM S + S_FREE", "mask + row max", "wait O_READY", "rescale (lazy)", "exp + pack + STTM", "st wait + P_FULL", "-"};
+#elif defined(XATTN_V6) || defined(XATTN_V7)
     const int step_keys = 64;
     const char* names[8] = {"wait S_FULL", "LDTM + wait", "max + rescale", "exp + pack + STTM", "st wait + P_FULL", "-", "-", "-"};
 #else
     const int step_keys = 128;
     const char* names[8] = {"wait S_FULL", "LDTM S + S_FREE", "mask + row max", "wait O_READY", "rescale (lazy)", "exp + pack + STTM", "st wait + P_FULL", "-"};
 #endif
-    const double tiles = (double)(tr[8] + tr[9]) * ((S + step_keys - 1) / step_keys);   // steps x traced warps
+    const double tiles = (double)(tr[8] + tr[9] + tr[10]) * ((S + step_keys - 1) / step_keys);   // steps x traced warps
     double tot = 0;
     for (int i = 0; i < 7; ++i) tot += tr[i] / tiles;
     for (int i = 0; i < 7; ++i) printf("  %-26s %8.1f cycles/step  (%4.1f%%)\n", names[i], tr[i] / tiles, 100.0 * tr[i] / tiles / tot);
