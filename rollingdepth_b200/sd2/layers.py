@@ -136,8 +136,11 @@ def _use_gemm_attention(q: torch.Tensor) -> bool:
     back to the sm80 memory-efficient kernel (175 TFLOP/s, 5.6 % of a `fast` step).  Two cuBLAS batched GEMMs with fp32
     logits + an fp32 softmax are ~2.5x faster and at least as accurate (P is rounded to 16 bits exactly like a fused
     kernel does)."""
-    return (_GEMM_ATTENTION_OK is not False and q.is_cuda and q.dtype in (torch.float16, torch.bfloat16)
-            and q.shape[1] == 1 and q.shape[-1] > 256)
+    if not (_GEMM_ATTENTION_OK is not False and q.is_cuda and q.dtype in (torch.float16, torch.bfloat16)
+            and q.shape[1] == 1 and q.shape[-1] > 256):
+        return False
+    # the fp32 logits are materialised ([B, S, S], twice with the softmax output): keep them below 24 GB
+    return q.shape[0] * q.shape[2] * q.shape[2] * 4 <= (24 << 30)
 
 
 def _wide_head_attention(q, k, v):

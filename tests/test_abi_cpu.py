@@ -128,3 +128,27 @@ def test_sharding_collectives_world2_gloo(tmp_path):
                        capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+def test_launch_share_tool_on_a_synthetic_ncu_csv(tmp_path, capsys):
+    """tools/launch_shares.py: shares of the LAST complete step (steps end with the renormalisation kernel)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("launch_shares", os.path.join(ROOT, "tools", "launch_shares.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    hdr = '"ID","Process ID","Process Name","Host Name","Kernel Name","Context","Stream","Block Size","Grid Size","Device","CC","Section Name","Metric Name","Metric Unit","Metric Value"'
+    def row(i, name, ns):
+        return f'"{i}","1","python","h","{name}","1","7","(256, 1, 1)","(1, 1, 1)","0","10.0","s","gpu__time_duration.sum","ns","{ns}"'
+    names = [("void rd::xattn_fwd_kernel<__half, 0>(int)", 1000), ("cudnn_conv(int)", 3000), ("void rd::renorm_kernel<__half>(int)", 10)]
+    lines = ["==PROF== header line", hdr]
+    i = 0
+    for rep in range(2):                        # two complete steps; the second has a slower attention launch
+        for n, ns in names:
+            lines.append(row(i, n, ns * (2 if (rep == 1 and "xattn" in n) else 1)))
+            i += 1
+    p = tmp_path / "launches.csv"
+    p.write_text("\n".join(lines) + "\n")
+    mod.main(str(p))
+    out = capsys.readouterr().out
+    assert "using launches 3..5" in out
+    assert "39.92%" in out and "*rd::xattn_fwd_kernel" in out       # 2000 / 5010
