@@ -12,14 +12,11 @@
 #include <cstdlib>
 #include <vector>
 
-#if defined(XATTN_V5)
-#include "attn_variants/xattn_v5.cu"      // copy of attn_variants/xattn_v5_*.cu.txt made by the build line (A/B runs)
-#elif defined(XATTN_V6)
-#include "attn_variants/xattn_v6.cu"
-#elif defined(XATTN_V8)
-#include "attn_variants/xattn_v8.cu"
+// archived variants (build with -I rollingdepth_b200/csrc; see attn_variants/README.md for their measurements)
+#if defined(XATTN_V6)
+#include "attn_variants/xattn_v6_64key_steps_double_buffered_prefetch.cu.txt"
 #elif defined(XATTN_V7)
-#include "attn_variants/xattn_v7.cu"      // build with -I rollingdepth_b200/csrc
+#include "attn_variants/xattn_v7_four_tiles_p_aliased_polling_issuer.cu.txt"
 #else
 #include "../../rollingdepth_b200/csrc/xattn_sm100.cu"
 #endif
@@ -74,13 +71,10 @@ int run(int B, int H, int S, int flags, int iters, rd_dtype dt) {
     ms /= iters;
     const double flops = 4.0 * B * H * (double)S * S * 64;
     printf("B=%d H=%d S=%d %s flags=%d: %.4f ms  %.1f TFLOP/s\n", B, H, S, dt == RD_F16 ? "f16" : "bf16", flags, ms, flops / ms / 1e9);
-#if defined(RD_XATTN_TRACE) && !defined(XATTN_V5)
+#if defined(RD_XATTN_TRACE)
     unsigned long long tr[16];
     cudaMemcpyFromSymbol(tr, rd::rd_xattn_trace, sizeof(tr));
-#if defined(XATTN_V8)
-    const int step_keys = 64;
-    const char* names[8] = {"wait S_FULL", "LDTM S + S_FREE", "mask + row max", "wait O_READY", "rescale (lazy)", "exp + pack + STTM", "st wait + P_FULL", "-"};
-#elif defined(XATTN_V6) || defined(XATTN_V7)
+#if defined(XATTN_V6) || defined(XATTN_V7)
     const int step_keys = 64;
     const char* names[8] = {"wait S_FULL", "LDTM + wait", "max + rescale", "exp + pack + STTM", "st wait + P_FULL", "-", "-", "-"};
 #else
