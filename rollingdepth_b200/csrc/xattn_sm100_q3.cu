@@ -25,7 +25,7 @@ namespace q3 {
 using namespace ptx;
 
 #ifdef RD_XATTN_TRACE
-// phase cycle counters of softmax warp 0 (summed over CTAs), read by tools/probes/xattn_bench.cu
+// phase cycle counters of the first warp of each softmax warpgroup (summed over CTAs), for tools/probes/xattn_bench.cu
 __device__ unsigned long long rd_xattn_trace[16];
 #define RD_TRACE_DECL long long tr_t = clock64(); unsigned long long tr_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define RD_TRACE(i) { const long long tr_n = clock64(); tr_acc[i] += (unsigned long long)(tr_n - tr_t); tr_t = tr_n; }
@@ -45,7 +45,7 @@ constexpr int kD = 64;         // head dim
 constexpr int kStages = 3;
 constexpr int kTileBytes = kBN * kD * 2;   // 16384
 constexpr int kSoftmaxThreads = kNQ * 128;
-constexpr int kThreads = kSoftmaxThreads + 128;   // third warpgroup: two MMA warps, TMA warp, one idle warp (register donors)
+constexpr int kThreads = kSoftmaxThreads + 128;   // last warpgroup: three MMA issuer warps + the TMA warp
 constexpr int kMmaWarp = kNQ * 4, kTmaWarp = kNQ * 4 + 3;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColTile = 160, kColS = 0, kColO = 64, kColP = 128;   // per tile: S 64, O 64, P 32 columns
@@ -140,13 +140,6 @@ __device__ __forceinline__ void ex2_poly2(uint64_t x2, float& p0, float& p1) {
     unpack2(p, q0, q1);
     p0 = __int_as_float(__float_as_int(t0) * (1 << 23) + __float_as_int(q0));
     p1 = __int_as_float(__float_as_int(t1) * (1 << 23) + __float_as_int(q1));
-}
-
-__device__ __forceinline__ void named_bar_sync(int id, int count) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
-}
-__device__ __forceinline__ void named_bar_arrive(int id, int count) {
-    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
 
 // row maximum of one 64-key step: 8 independent chains of 3-input max (one dependent chain would be ~250 cycles)
