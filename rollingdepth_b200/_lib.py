@@ -120,6 +120,21 @@ def check(code: int, what: str) -> None:
         raise RdError(f"{what} failed with status {code}: {msg}")
 
 
+def device_guard(device: torch.device):
+    """Context manager making `device` the CURRENT CUDA device: the C ABI launches on the calling thread's current
+    device (kernel attributes and the SM count are cached per device ordinal inside the library), while tensors
+    and the stream come from `device` -- without the guard a pipeline living on cuda:1 in a process whose current
+    device is cuda:0 would launch on the wrong GPU."""
+    return torch.cuda.device(device)
+
+
+def call(name: str, device: torch.device, *args) -> None:
+    """lib().<name>(*args) with `device` current; raises RdError on a non-zero status."""
+    with torch.cuda.device(device):
+        code = getattr(lib(), name)(*args)
+    check(code, name)
+
+
 def dtype_code(dt: torch.dtype) -> int:
     try:
         return _DTYPES[dt]

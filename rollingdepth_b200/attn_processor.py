@@ -46,8 +46,7 @@ class B200XFrameAttnProcessor:
     ) -> torch.Tensor:
         if attention_mask is not None:
             raise NotImplementedError("B200XFrameAttnProcessor: attention masks are not used on the RollingDepth path")
-        if not hidden_states.is_cuda:
-            raise L.RdError("B200XFrameAttnProcessor needs CUDA tensors (no CPU fallback)")
+        L.require_cuda(hidden_states)       # no CPU fallback
 
         residual = hidden_states
         if getattr(attn, "spatial_norm", None) is not None:

@@ -858,10 +858,10 @@ template <typename T, int RM, int NT, int NCTA>
 static int launch_pass_c(const PassParams& pp, dim3 grid, cudaStream_t st) {
     auto kern = coalign_pass_kernel<T, RM, NT, NCTA>;
     const int smem = pp.R * pp.px_per_chunk * (int)sizeof(T);
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce configured;      // cudaFuncSetAttribute is per device and not a stream operation
+    if (configured.needed()) {
         RD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPassSmemBudgetMax + 1024));
-        configured = true;
+        configured.done();
     }
     kern<<<grid, NT, smem, st>>>(pp);
     RD_LAUNCH_CHECK("coalign_pass_kernel");

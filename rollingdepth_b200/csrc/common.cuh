@@ -35,7 +35,17 @@ int cuda_fail(cudaError_t e, const char* what);
         if (_e != cudaSuccess) return rd::cuda_fail(_e, what);      \
     } while (0)
 
-int num_sms();
+int num_sms();            // SM count of the CURRENT device (cached per device ordinal)
+int current_device();     // cudaGetDevice; -1 on error
+
+// One-time per-DEVICE configuration of a kernel (cudaFuncSetAttribute is per device, not per process):
+//   static PerDeviceOnce once;  if (once.needed()) { RD_CUDA(cudaFuncSetAttribute(...)); once.done(); }
+constexpr int kMaxDevices = 64;
+struct PerDeviceOnce {
+    bool flag[kMaxDevices] = {};
+    bool needed() const { const int d = current_device(); return d < 0 || d >= kMaxDevices || !flag[d]; }
+    void done() { const int d = current_device(); if (d >= 0 && d < kMaxDevices) flag[d] = true; }
+};
 
 // ---------------------------------------------------------------- dtype helpers
 template <typename T> struct Cvt;

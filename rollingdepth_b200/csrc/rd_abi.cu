@@ -20,15 +20,21 @@ int cuda_fail(cudaError_t e, const char* what) {
     return RD_ERR_CUDA;
 }
 
+int current_device() {
+    int dev = 0;
+    return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
 int num_sms() {
-    static int cached = 0;
-    if (cached == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    static int cached[kMaxDevices] = {};
+    const int dev = current_device();
+    if (dev < 0 || dev >= kMaxDevices) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-        cached = n;
+        cached[dev] = n;
     }
-    return cached;
+    return cached[dev];
 }
 
 }  // namespace rd

@@ -460,10 +460,10 @@ static int launch_k(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensor
                     cudaStream_t st) {
     auto kern = xattn_fwd_kernel<T, POLY, PINGPONG, SPLIT>;
     const int smem = XattnSmem::bytes + 1024;
-    static bool configured = false;      // per instantiation; cudaFuncSetAttribute is not a stream operation
-    if (!configured) {
+    static PerDeviceOnce configured;      // cudaFuncSetAttribute is per device and not a stream operation
+    if (configured.needed()) {
         RD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        configured.done();
     }
     kern<<<grid, kThreads, smem, st>>>(mq, mk, mv, prm);
     RD_LAUNCH_CHECK("xattn_fwd_kernel");

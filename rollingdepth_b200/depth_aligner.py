@@ -52,6 +52,11 @@ class DepthAligner:
         self.loss_scale = loss_scale
         # filled by run(): device tensor [2] = (min, max) of the merged video (fp32)
         self.merged_minmax: Optional[torch.Tensor] = None
+        # multi-GPU (set by the pipeline, see sharding.py): with `shard.world > 1` and optimizer_mode == "allreduce"
+        # the optimiser runs frame-sharded with a per-iteration all-reduce; "replicated" runs the single-GPU loop on
+        # every rank (inputs are identical on every rank after the snippet all-gather, so are the results)
+        self.shard = None
+        self.optimizer_mode = "replicated"
 
     # ------------------------------------------------------------------ helpers
     def create_triplet_indices(self, sequence_length: int, gap: int, window_size: int) -> torch.Tensor:
@@ -100,9 +105,9 @@ class DepthAligner:
         dev_min = torch.empty(1, dtype=torch.float32, device=dev)
         ptrs = L.ptr_array(snips)
         st = L.stream_ptr(dev)
-        L.check(lib.rd_global_min(ptrs, C.byref(pb), L.ptr(dev_min), L.ptr(scratch), st), "rd_global_min")
+        L.call("rd_global_min", dev, ptrs, C.byref(pb), L.ptr(dev_min), L.ptr(scratch), st)
         x_small = torch.empty((pb.n_total, pb.w, pb.P_pad), dtype=dt, device=dev)
-        L.check(lib.rd_coalign_prep(ptrs, C.byref(pb), L.ptr(dev_min), L.ptr(x_small), st), "rd_coalign_prep")
+        L.call("rd_coalign_prep", dev, ptrs, C.byref(pb), L.ptr(dev_min), L.ptr(x_small), st)
         L.count_launches(2)
         return pb, snips, dev_min, x_small
 
@@ -124,9 +129,8 @@ class DepthAligner:
             L.check(int(ws_bytes), "rd_coalign_workspace_bytes")
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         hist = torch.empty((max(n_iter, 1), 3), dtype=torch.float32, device=dev)
-        L.check(lib.rd_coalign_optimize(L.ptr(x_small), C.byref(pb), C.byref(hp), *[L.ptr(a) for a in state],
-                                        int(step0), int(n_iter), L.ptr(hist), L.ptr(ws), ws_bytes, L.stream_ptr(dev)),
-                "rd_coalign_optimize")
+        L.call("rd_coalign_optimize", dev, L.ptr(x_small), C.byref(pb), C.byref(hp), *[L.ptr(a) for a in state],
+               int(step0), int(n_iter), L.ptr(hist), L.ptr(ws), ws_bytes, L.stream_ptr(dev))
         L.count_launches(n_iter + 2)      # one fused pass per iteration + final update + history reduction
         return hist[:n_iter]
 
@@ -137,8 +141,8 @@ class DepthAligner:
         merged = torch.empty((pb.N, 1, pb.H, pb.W), dtype=snips[0].dtype, device=dev)
         self.merged_minmax = torch.empty(2, dtype=torch.float32, device=dev)
         scratch = torch.empty(lib.rd_reduce_scratch_bytes(), dtype=torch.uint8, device=dev)
-        L.check(lib.rd_merge(L.ptr_array(snips), C.byref(pb), L.ptr(dev_min), L.ptr(s), L.ptr(t), L.ptr(merged),
-                             L.ptr(self.merged_minmax), L.ptr(scratch), L.stream_ptr(dev)), "rd_merge")
+        L.call("rd_merge", dev, L.ptr_array(snips), C.byref(pb), L.ptr(dev_min), L.ptr(s), L.ptr(t), L.ptr(merged),
+               L.ptr(self.merged_minmax), L.ptr(scratch), L.stream_ptr(dev))
         L.count_launches(1)
         return merged
 
@@ -154,7 +158,11 @@ class DepthAligner:
         if not bool(covered.all()):
             logging.warning("Not every frame is covered by a snippet; uncovered frames are NaN (as in the reference)")
         state = self.new_state(pb)
-        hist = self.optimize_state(pb, x_small, state, 0, int(self.num_iterations))
+        if self.shard is not None and self.shard.world > 1 and self.optimizer_mode == "allreduce":
+            from .sharding import coalign_optimize_allreduce
+            hist = coalign_optimize_allreduce(self, self.shard, pb, x_small, state, int(self.num_iterations))
+        else:
+            hist = self.optimize_state(pb, x_small, state, 0, int(self.num_iterations))
         merged = self.merge(pb, snips, dev_min, state[0], state[1])
         scales = [state[0][pb.row0[g]: pb.row0[g] + pb.n[g]].reshape(-1, 1, 1) for g in range(pb.G)]
         translations = [state[1][pb.row0[g]: pb.row0[g] + pb.n[g]].reshape(-1, 1, 1) for g in range(pb.G)]

@@ -33,14 +33,13 @@ def xattn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: Optional
     if out is None:
         out = torch.empty((B, Sq, H, D), dtype=q.dtype, device=q.device)
     scale = (1.0 / math.sqrt(D)) if scale is None else float(scale)
-    code = L.lib().rd_xattn_fwd(
-        L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(out), B, H, Sq, Sk, D,
+    L.call(
+        "rd_xattn_fwd", q.device, L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(out), B, H, Sq, Sk, D,
         q.stride(0), q.stride(1), q.stride(2),
         k.stride(0), k.stride(1), k.stride(2),
         v.stride(0), v.stride(1), v.stride(2),
         out.stride(0), out.stride(1), out.stride(2),
         L.dtype_code(q.dtype), scale, int(flags), L.stream_ptr(q.device))
-    L.check(code, "rd_xattn_fwd")
     L.count_launches(1)
     return out
 
@@ -58,10 +57,9 @@ def ddim_step(model_output: torch.Tensor, sample: torch.Tensor, sqrt_alpha_t: fl
     mo, sm = model_output.contiguous(), sample.contiguous()
     if out is None:
         out = torch.empty_like(sm)
-    code = L.lib().rd_ddim_step(L.ptr(mo), L.ptr(sm), L.ptr(out), sm.numel(), sqrt_alpha_t, sqrt_beta_t,
-                                sqrt_alpha_prev, sqrt_one_minus_alpha_prev, _PTYPE[prediction_type], float(clip),
-                                L.dtype_code(sm.dtype), L.stream_ptr(sm.device))
-    L.check(code, "rd_ddim_step")
+    L.call("rd_ddim_step", sm.device, L.ptr(mo), L.ptr(sm), L.ptr(out), sm.numel(), sqrt_alpha_t, sqrt_beta_t,
+           sqrt_alpha_prev, sqrt_one_minus_alpha_prev, _PTYPE[prediction_type], float(clip),
+           L.dtype_code(sm.dtype), L.stream_ptr(sm.device))
     L.count_launches(1)
     return out
 
@@ -72,9 +70,8 @@ def ddim_add_noise(original: torch.Tensor, noise: torch.Tensor, sqrt_alpha_prod:
     L.require_cuda(original, noise)
     x, n = original.contiguous(), noise.contiguous()
     out = torch.empty_like(x)
-    code = L.lib().rd_ddim_add_noise(L.ptr(x), L.ptr(n), L.ptr(out), x.numel(), sqrt_alpha_prod,
-                                     sqrt_one_minus_alpha_prod, L.dtype_code(x.dtype), L.stream_ptr(x.device))
-    L.check(code, "rd_ddim_add_noise")
+    L.call("rd_ddim_add_noise", x.device, L.ptr(x), L.ptr(n), L.ptr(out), x.numel(), sqrt_alpha_prod,
+           sqrt_one_minus_alpha_prod, L.dtype_code(x.dtype), L.stream_ptr(x.device))
     L.count_launches(1)
     return out
 
@@ -84,9 +81,8 @@ def renorm_(depth: torch.Tensor, minmax: torch.Tensor) -> torch.Tensor:
     L.require_cuda(depth, minmax)
     if not depth.is_contiguous():
         raise L.RdError("renorm_ needs a contiguous tensor")
-    code = L.lib().rd_renorm(L.ptr(depth), depth.numel(), L.ptr(minmax), L.dtype_code(depth.dtype),
-                             L.stream_ptr(depth.device))
-    L.check(code, "rd_renorm")
+    L.call("rd_renorm", depth.device, L.ptr(depth), depth.numel(), L.ptr(minmax), L.dtype_code(depth.dtype),
+           L.stream_ptr(depth.device))
     L.count_launches(1)
     return depth
 
@@ -122,9 +118,8 @@ def group_norm_nhwc(x: torch.Tensor, num_groups: int, weight: Optional[torch.Ten
     if pre is not None and tuple(pre.shape) != (N, Cc):
         raise L.RdError(f"pre_add must be [{N}, {Cc}], got {tuple(pre.shape)}")
     P = lambda t: L.ptr(t) if t is not None else None
-    code = lib.rd_groupnorm_nhwc(L.ptr(x), L.ptr(y), P(g), P(b), P(pre), N, HW, Cc, int(num_groups), float(eps),
-                                 1 if silu else 0, L.dtype_code(x.dtype), L.ptr(ws), ws_bytes, L.stream_ptr(x.device))
-    L.check(code, "rd_groupnorm_nhwc")
+    L.call("rd_groupnorm_nhwc", x.device, L.ptr(x), L.ptr(y), P(g), P(b), P(pre), N, HW, Cc, int(num_groups), float(eps),
+           1 if silu else 0, L.dtype_code(x.dtype), L.ptr(ws), ws_bytes, L.stream_ptr(x.device))
     L.count_launches(2)
     return y
 
@@ -141,9 +136,8 @@ def bias_residual_nhwc(x: torch.Tensor, bias: Optional[torch.Tensor] = None, vec
     y = x if inplace else torch.empty_like(x)
     b, v = _opt(bias, x.dtype), _opt(vec, x.dtype)
     P = lambda t: L.ptr(t) if t is not None else None
-    code = L.lib().rd_bias_residual_nhwc(L.ptr(x), P(b), P(v), P(residual), L.ptr(y), N, HW, Cc, L.dtype_code(x.dtype),
-                                         L.stream_ptr(x.device))
-    L.check(code, "rd_bias_residual_nhwc")
+    L.call("rd_bias_residual_nhwc", x.device, L.ptr(x), P(b), P(v), P(residual), L.ptr(y), N, HW, Cc,
+           L.dtype_code(x.dtype), L.stream_ptr(x.device))
     L.count_launches(1)
     return y
 
@@ -156,9 +150,8 @@ def upsample_nearest_nhwc(x: torch.Tensor, size) -> torch.Tensor:
     N, Cc, H, W = x.shape
     Ho, Wo = int(size[0]), int(size[1])
     y = torch.empty((N, Cc, Ho, Wo), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
-    code = L.lib().rd_upsample_nearest_nhwc(L.ptr(x), L.ptr(y), N, H, W, Ho, Wo, Cc, L.dtype_code(x.dtype),
-                                            L.stream_ptr(x.device))
-    L.check(code, "rd_upsample_nearest_nhwc")
+    L.call("rd_upsample_nearest_nhwc", x.device, L.ptr(x), L.ptr(y), N, H, W, Ho, Wo, Cc, L.dtype_code(x.dtype),
+           L.stream_ptr(x.device))
     L.count_launches(1)
     return y
 
@@ -171,7 +164,6 @@ def geglu(proj: torch.Tensor) -> torch.Tensor:
     D = proj.shape[-1] // 2
     M = proj.numel() // (2 * D)
     y = torch.empty(*proj.shape[:-1], D, dtype=proj.dtype, device=proj.device)
-    code = L.lib().rd_geglu(L.ptr(proj), L.ptr(y), M, D, L.dtype_code(proj.dtype), L.stream_ptr(proj.device))
-    L.check(code, "rd_geglu")
+    L.call("rd_geglu", proj.device, L.ptr(proj), L.ptr(y), M, D, L.dtype_code(proj.dtype), L.stream_ptr(proj.device))
     L.count_launches(1)
     return y

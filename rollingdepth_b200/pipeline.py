@@ -9,9 +9,11 @@ rollingdepth/rollingdepth_pipeline.py (cited per method); what changes is the me
     per batch element, SURVEY.md App. D Q2) instead of one by one (:415-446);
   * the DDIM algebra is one fused kernel per step with host-side schedule scalars (no per-step sync);
   * co-alignment / merge / re-normalisation run in the fused kernels of `DepthAligner`;
-  * with `torch.distributed` initialised (one process per GPU) the snippet list of every dilation is
-    block-partitioned over the ranks ("snippet sharding"); NCCL carries only small tensors (rgb latents,
-    subsampled predictions, per-frame partial sums of the merge, refined latents).
+  * with `torch.distributed` initialised (one process per GPU, `enable_sharding()`) the flattened (dilation, snippet)
+    list is block-partitioned over the ranks ("snippet sharding", sharding.py); one in-place NCCL all-gather per stage
+    (rgb latents, decoded snippets, refined latents, final depth) and nothing else crosses NVLink.  After the snippet
+    gather every rank holds every snippet, so co-alignment / merge run the single-GPU kernels and the result is
+    bit-identical to a one-GPU run; only `output_ranks` (default: rank 0) copy results to the host.
 
 There is no CPU fallback: the pipeline must live on a CUDA device.
 """
@@ -29,14 +31,15 @@ from . import ops
 from .attn_processor import B200XFrameAttnProcessor
 from .depth_aligner import DepthAligner
 from .scheduler import DDIMSchedule
-from .sharding import Shard
+from .sharding import Shard, balanced_chunks
 
 
 _HOST_POOL = None
 
 
 def _host_copy_pool(world: int = 1):
-    """Worker threads for the host-side result copies (torch's copy releases the GIL)."""
+    """Worker threads for the host-side result copies (torch's copy releases the GIL); `world` = number of
+    processes on this box that copy results (the output ranks)."""
     global _HOST_POOL
     if _HOST_POOL is None:
         from concurrent.futures import ThreadPoolExecutor
@@ -70,6 +73,8 @@ class RollingDepthPipeline:
         self.empty_text_embed: torch.Tensor = None  # type: ignore
         self.snippet_batch = int(snippet_batch)
         self.shard = Shard()            # single rank unless torch.distributed is initialised (see enable_sharding)
+        self.output_ranks = None        # ranks that copy results to the host (None = every rank)
+        self.coalign_mode = "replicated"
         self.timings: Dict[str, float] = {}
         self.channels_last, self.fused_norm = bool(channels_last), bool(fused_norm)
         self._tuned_for = None
@@ -78,6 +83,8 @@ class RollingDepthPipeline:
         self._stage_slot = 0
         self._stage_events: Dict[int, torch.cuda.Event] = {}
         self._host_copies: list = []
+        self._copy_stream = None        # side stream for device -> host result copies (overlaps the remaining compute)
+        self._keepalive: list = []
         if install_processor:
             self.unet.set_attn_processor(B200XFrameAttnProcessor())
         logging.debug(f"Pipeline initialized: {type(self)}")
@@ -126,10 +133,25 @@ class RollingDepthPipeline:
         ev = getattr(self, "stage_events", None) or []
         return [(ev[i + 1][0], ev[i][1].elapsed_time(ev[i + 1][1])) for i in range(len(ev) - 1)]
 
-    def enable_sharding(self, group=None) -> "RollingDepthPipeline":
-        """Shard snippets over the ranks of `group` (default: the world group)."""
+    def enable_sharding(self, group=None, output_ranks=(0,), coalign_mode: str = "replicated") -> "RollingDepthPipeline":
+        """Shard frames / snippets / refinement windows over the ranks of `group` (default: the world group).
+
+        `output_ranks`: the ranks whose `forward` returns the complete `RollingDepthOutput` on the host, exactly as a
+        single-GPU call would (default rank 0); the other ranks return an output whose fields are None -- copying
+        ~1 GB of identical results to the host on every rank was the largest non-sharded cost at 8 GPUs.  `None` =
+        every rank returns the complete result.
+        `coalign_mode`: "replicated" (every rank runs the 2000-iteration optimiser on the gathered snippets; bit-identical
+        everywhere, no per-iteration exchange) or "allreduce" (frames of the optimiser block-partitioned, per-iteration
+        all-reduce of the per-(frame, contribution) gradient terms -- same parameters bit for bit)."""
+        if coalign_mode not in ("replicated", "allreduce"):
+            raise ValueError(f"unknown coalign_mode {coalign_mode!r}")
         self.shard = Shard.from_dist(group)
+        self.output_ranks = None if output_ranks is None else tuple(int(r) for r in output_ranks)
+        self.coalign_mode = coalign_mode
         return self
+
+    def _is_output_rank(self) -> bool:
+        return self.shard.world == 1 or self.output_ranks is None or self.shard.rank in self.output_ranks
 
     # ------------------------------------------------------------------ __call__ (rollingdepth_pipeline.py:78-176)
     @torch.no_grad()
@@ -246,10 +268,23 @@ class RollingDepthPipeline:
         # pipeline dtype on the device gives the same values (one round-to-nearest either way) without the CPU pass
         if getattr(self, "stage_events", None) is not None:
             self.stage_events = []
+        self._stage_slot = 0
+        self._stage_events = {}
+        self._keepalive = []
+        is_out = self._is_output_rank()
         self._mark("start")
-        input_frames = input_frames.to(device, non_blocking=True).to(self.dtype)
+        if self.shard.world > 1 and not is_out and not input_frames.is_cuda:
+            # a rank that returns nothing needs only its own block of frames (for the sharded VAE encode)
+            f_lo, f_hi = self.shard.block(seq_len)
+            frames_dev = input_frames[:, f_lo:f_hi].to(device, non_blocking=True).to(self.dtype)
+            frame_block = (f_lo, f_hi)
+        else:
+            frames_dev = input_frames.to(device, non_blocking=True).to(self.dtype)
+            frame_block = None
         self._mark("h2d+cast")
-        rgb_latent = self.encode_rgb(input_frames, max_batch_size=max_vae_bs, verbose=verbose, sharded=True)
+        out_rgb = self._to_host(frames_dev.squeeze(0) / 2.0 + 0.5) if is_out else None      # :349
+        rgb_latent = self.encode_rgb(frames_dev, max_batch_size=max_vae_bs, verbose=verbose, sharded=True,
+                                     frame_block=frame_block, total_frames=seq_len)
         self._mark("vae_encode(+gather)")
         if self.empty_text_embed is None:
             self.encode_empty_text()
@@ -268,21 +303,23 @@ class RollingDepthPipeline:
             rgb_latent=rgb_latent, init_noise=init_noise, dilations=dilations, cap_dilation=cap_dilation,
             snippet_lengths=snippet_lengths, init_infer_steps=init_infer_steps, strides=strides,
             max_vae_bs=max_vae_bs, unload_snippet=unload_snippet, verbose=verbose)
+        # the decoded snippets are final: their device -> host copies overlap co-alignment (and refinement)
+        out_snips = [self._to_host(snippet) for snippet in snippet_pred_ls] if is_out else None
 
         # ----------------- Co-alignment (:304-318) -----------------
+        # sharded runs: every rank holds every snippet after the gather in init_snippet_infer, so the aligner is the
+        # single-GPU one (replicated, bit-identical on every rank) unless coalign_mode == "allreduce"
         coalign_kwargs = {} if coalign_kwargs is None else coalign_kwargs
         depth_aligner = DepthAligner(verbose=verbose, device=device, **coalign_kwargs)
-        if self.shard.world > 1:
-            from .sharding import sharded_coalign
-            depth_coaligned, scales, translations, loss_history, snippet_pred_ls = sharded_coalign(
-                depth_aligner, self.shard, snippet_pred_ls, dilations, seq_len, snippet_lengths[0])
-        else:
-            depth_coaligned, scales, translations, loss_history = depth_aligner.run(
-                snippet_ls=snippet_pred_ls, dilations=dilations)
+        depth_aligner.shard, depth_aligner.optimizer_mode = self.shard, self.coalign_mode
+        depth_coaligned, scales, translations, loss_history = depth_aligner.run(
+            snippet_ls=snippet_pred_ls, dilations=dilations)
         self.last_alignment = (scales, translations, loss_history)
+        self.last_minmax = depth_aligner.merged_minmax          # (min, max) of the merged video before re-normalisation
         # d -= d.min(); d /= d.max(); d = d*2-1, min/max come fused out of the merge kernel
         ops.renorm_(depth_coaligned, depth_aligner.merged_minmax)
-        self._mark("coalign(+exchange)+merge+renorm")
+        self._mark("coalign+merge+renorm")
+        out_coal = self._to_host(depth_coaligned.squeeze(0)) if is_out else None
 
         # ----------------- Refinement (:322-345) -----------------
         if refine_step > 0:
@@ -296,23 +333,21 @@ class RollingDepthPipeline:
             depth_pred = self.decode_depth(depth_latent_new, max_batch_size=max_vae_bs, verbose=verbose, sharded=True)
         else:
             depth_pred = depth_coaligned
+        out_pred = self._to_host(depth_pred.squeeze(0)) if is_out else None     # a separate host tensor, as :348/:352
+        self._mark("refine+decode")
 
         # ----------------- Output (:347-354): everything to the host -----------------
         # The reference's `.cpu()` calls return fresh pageable tensors.  Page-locking ~1 GB of fresh host memory per call
         # (torch.empty(pin_memory=True)) cost 0.65 s of a 5.8 s step, so the device -> host copies go asynchronously
-        # into pipeline-owned pinned staging buffers (allocated once, reused by every call) and, after ONE
-        # synchronisation, are copied on the host into fresh pageable tensors (reference semantics).
-        # `output_mode = "pinned_views"` skips that host copy and returns views of the staging buffers, valid until the
-        # next call of this pipeline object.
-        self._stage_slot = 0
-        self._stage_events = {}
-        out = RollingDepthOutput(
-            input_rgb=self._to_host(input_frames.squeeze(0) / 2.0 + 0.5),
-            depth_pred=self._to_host(depth_pred.squeeze(0)),
-            snippet_ls=[self._to_host(snippet) for snippet in snippet_pred_ls],
-            depth_coaligned=self._to_host(depth_coaligned.squeeze(0)),
-        )
-        self._mark("refine+outputs_d2h")
+        # (on a side stream, as soon as each tensor is final) into pipeline-owned pinned staging buffers (allocated
+        # once, reused by every call) and are then copied on the host into fresh pageable tensors (reference
+        # semantics).  `output_mode = "pinned_views"` skips that host copy and returns views of the staging buffers,
+        # valid until the next call of this pipeline object.
+        if not is_out:
+            torch.cuda.current_stream(device).synchronize()
+            self._keepalive = []
+            return RollingDepthOutput(input_rgb=None, depth_pred=None, snippet_ls=None, depth_coaligned=None)
+        out = RollingDepthOutput(input_rgb=out_rgb, depth_pred=out_pred, snippet_ls=out_snips, depth_coaligned=out_coal)
         if self.output_mode != "pinned_views":
             # host copies start as soon as the corresponding transfer has landed (per-tensor events)
             out = RollingDepthOutput(
@@ -320,16 +355,22 @@ class RollingDepthPipeline:
                 snippet_ls=[self._detach_host(t) for t in out.snippet_ls],
                 depth_coaligned=self._detach_host(out.depth_coaligned))
         torch.cuda.current_stream(device).synchronize()
+        if self._copy_stream is not None:
+            self._copy_stream.synchronize()
         for fut in self._host_copies:
             fut.result()
         self._host_copies = []
+        self._keepalive = []
+        self._mark("outputs_d2h")
         return out
 
     def _to_host(self, t: torch.Tensor) -> torch.Tensor:
-        """Asynchronous device -> host copy into the next pinned staging buffer of this pipeline."""
+        """Asynchronous device -> host copy into the next pinned staging buffer of this pipeline, issued on a side
+        stream behind an event of the producing stream so that it overlaps whatever the pipeline computes next."""
         if not t.is_cuda:
             return t
         t = t.contiguous()
+        self._keepalive.append(t)           # the allocator must not hand this block out again before the copy has run
         nbytes = t.numel() * t.element_size()
         slot = self._stage_slot
         self._stage_slot += 1
@@ -340,9 +381,15 @@ class RollingDepthPipeline:
             buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, device="cpu", pin_memory=True)
             self._staging[slot] = buf
         host = buf[:nbytes].view(t.dtype).view(t.shape)
-        host.copy_(t, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record()
+        if self._copy_stream is None or self._copy_stream.device != t.device:
+            self._copy_stream = torch.cuda.Stream(device=t.device)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(t.device))
+        with torch.cuda.stream(self._copy_stream):
+            self._copy_stream.wait_event(ready)
+            host.copy_(t, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
         self._stage_events[host.data_ptr()] = ev
         return host
 
@@ -360,7 +407,8 @@ class RollingDepthPipeline:
         if nbytes < (16 << 20) or rows < 2:
             out.copy_(t)
             return out
-        pool = _host_copy_pool(self.shard.world)
+        n_out = self.shard.world if self.output_ranks is None else max(1, len(self.output_ranks))
+        pool = _host_copy_pool(n_out)
         n_blk = min(rows, 4 * pool._max_workers)
         step = (rows + n_blk - 1) // n_blk
         for r0 in range(0, rows, step):
@@ -370,39 +418,54 @@ class RollingDepthPipeline:
     # ------------------------------------------------------------------ initial snippet inference (:356-463)
     def init_snippet_infer(self, rgb_latent, init_noise, dilations, cap_dilation, snippet_lengths, init_infer_steps,
                            strides, max_vae_bs, unload_snippet, verbose) -> List[torch.Tensor]:
+        """Returns, on EVERY rank, the decoded snippets of every dilation ([n_d, n, 1, H, W] each).
+
+        Dilations that share (snippet length, number of denoise steps) -- all of them in every preset -- form one
+        group whose snippets are flattened into a single list; that list is block-partitioned over the ranks
+        (sharding.py), denoised in balanced batches, decoded in balanced chunks straight into this rank's slot of
+        the gather buffer and exchanged with one in-place all-gather."""
         B, seq_len, _, h, w = rgb_latent.shape
         if 1 != B:
             raise NotImplementedError("RollingDepth is implemented for B=1")
         text = self.empty_text_embed.to(self.device)            # [1, 2, C]
-        snippet_pred_ls = []
-        for dilation, snippet_len, stride, init_infer_step in zip(dilations, snippet_lengths, strides, init_infer_steps):
-            timesteps = self.scheduler.set_timesteps(init_infer_step)
-            snippet_idx_ls = self.get_snippet_indice(
-                i_step=0, timesteps=timesteps, seq_len=seq_len, snippet_len=snippet_len,
-                dilation_start=dilation, dilation_end=dilation, stride=stride)
-            lo, hi = self.shard.block(len(snippet_idx_ls))      # this rank's contiguous block of snippets
-            mine = snippet_idx_ls[lo:hi]
-            latents = []
-            for b0 in range(0, len(mine), self.snippet_batch):
-                idx = torch.tensor(mine[b0:b0 + self.snippet_batch], device=self.device)      # [b, n]
+        H, W = self._decoded_hw(h, w)
+        per_dil: List[Optional[torch.Tensor]] = [None] * len(dilations)
+        groups: Dict[tuple, List[int]] = {}
+        for gi, (snippet_len, n_steps) in enumerate(zip(snippet_lengths, init_infer_steps)):
+            groups.setdefault((snippet_len, n_steps), []).append(gi)
+        for (snippet_len, n_steps), members in groups.items():
+            timesteps = self.scheduler.set_timesteps(n_steps)
+            flat: List[List[int]] = []
+            spans = []
+            for gi in members:
+                idx_ls = self.get_snippet_indice(
+                    i_step=0, timesteps=timesteps, seq_len=seq_len, snippet_len=snippet_len,
+                    dilation_start=dilations[gi], dilation_end=dilations[gi], stride=strides[gi])
+                spans.append((gi, len(flat), len(flat) + len(idx_ls)))
+                flat.extend(idx_ls)
+            n_flat = len(flat)
+            lo, hi = self.shard.block(n_flat)                   # this rank's contiguous block of the flat list
+            tag = ",".join(str(dilations[gi]) for gi in members)
+            latents = torch.empty((hi - lo, snippet_len, 4, h, w), device=self.device, dtype=self.dtype)
+            for b0, b1 in balanced_chunks(hi - lo, self.snippet_batch):
+                idx = torch.tensor(flat[lo + b0: lo + b1], device=self.device)      # [b, n]
                 rgb_snip = rgb_latent[0, idx]                     # [b, n, 4, h, w] (gather copy, :417)
                 depth_snip = init_noise[0, idx].contiguous()
-                for t in timesteps:
+                for i_t, t in enumerate(timesteps):
                     pred = self.single_step(rgb_snip, depth_snip, t, text)
-                    depth_snip = self.scheduler.step(pred, t, depth_snip)
-                latents.append(depth_snip)
-            self._mark(f"unet+ddim d={dilation}")
-            if latents:
-                depth_snippet_latent = torch.cat(latents, dim=0)  # [n_mine, n, 4, h, w]
-                decoded = self.decode_depth(depth_snippet_latent, max_batch_size=max_vae_bs, verbose=verbose)
-            else:
-                H, W = self._decoded_hw(h, w)
-                decoded = torch.empty((0, snippet_len, 1, H, W), device=self.device, dtype=self.dtype)
-            self._mark(f"vae_decode d={dilation}")
-            if unload_snippet:
-                decoded = decoded.cpu()
-            snippet_pred_ls.append(decoded)
-        return snippet_pred_ls
+                    last = i_t == len(timesteps) - 1
+                    depth_snip = self.scheduler.step(pred, t, depth_snip, out=latents[b0:b1] if last else None)
+            self._mark(f"unet+ddim d={tag}")
+            buf, mine = self.shard.gather_buffer(n_flat, (snippet_len, 1, H, W), self.dtype, self.device)
+            if hi > lo:
+                self.decode_depth(latents, max_batch_size=max_vae_bs, verbose=verbose, out=mine)
+            self._mark(f"vae_decode d={tag}")
+            decoded = self.shard.gather_(buf, n_flat)
+            if self.shard.world > 1:
+                self._mark(f"snippet_gather d={tag}")
+            for gi, a, b in spans:
+                per_dil[gi] = decoded[a:b].cpu() if unload_snippet else decoded[a:b]
+        return per_dil      # type: ignore[return-value]
 
     def _decoded_hw(self, h, w):
         f = 2 ** (len(self.vae.decoder.up_blocks) - 1)
@@ -460,16 +523,14 @@ class RollingDepthPipeline:
             g = snippet_idx_ls[0][1] - snippet_idx_ls[0][0] if snippet_len > 1 else 1
             depth_latent_old = depth_latent_new                     # every window reads the OLD latent (:605)
             lo, hi = self.shard.block(n_win)
-            preds = torch.empty((n_win, snippet_len, 4, h, w), device=self.device, dtype=self.dtype)
-            for b0 in range(lo, hi, self.snippet_batch):
-                b1 = min(b0 + self.snippet_batch, hi)
-                idx = torch.tensor(snippet_idx_ls[b0:b1], device=self.device)
+            buf, mine = self.shard.gather_buffer(n_win, (snippet_len, 4, h, w), self.dtype, self.device)
+            for b0, b1 in balanced_chunks(hi - lo, self.snippet_batch):
+                idx = torch.tensor(snippet_idx_ls[lo + b0: lo + b1], device=self.device)
                 rgb_in = rgb_latent[0, idx]
                 depth_in = depth_latent_old[0, idx]
                 pred = self.single_step(rgb_in, depth_in, t_current, text)
-                self.scheduler.step(pred, t_current, depth_in, out=preds[b0:b1])
-            if self.shard.world > 1:
-                preds = self.shard.all_gather_blocks(preds, n_win)
+                self.scheduler.step(pred, t_current, depth_in, out=mine[b0:b1])
+            preds = self.shard.gather_(buf, n_win)
             # accumulate per frame in the reference's order (windows by ascending start => j = n-1 ... 0), with the
             # reference's in-dtype rounding after every += (:621-624), then average by the integer count (:629)
             new = torch.zeros_like(depth_latent_old[0])
@@ -477,8 +538,11 @@ class RollingDepthPipeline:
             for j in range(snippet_len - 1, -1, -1):
                 new[j * g: j * g + n_win] += preds[:, j]
                 count[j * g: j * g + n_win] += 1
-            # coverage is pure index logic: check it on the host instead of syncing on `count` (:628)
-            assert (snippet_len - 1) * g + n_win == seq_len, "refinement windows do not cover every frame"
+            # `assert torch.all(count_depth_latent_new > 0)` (:628) is pure index logic: frame f is covered iff
+            # f - j*g lies in [0, n_win) for some j, i.e. the w blocks [j*g, j*g + n_win) leave no gap -- checked on
+            # the host instead of synchronising on `count`
+            assert snippet_len == 1 and n_win == seq_len or snippet_len > 1 and n_win >= g, \
+                "refinement windows do not cover every frame"
             depth_latent_new = (new / count[:, None, None, None])[None]
         return depth_latent_new
 
@@ -497,46 +561,61 @@ class RollingDepthPipeline:
         return noise_pred.unflatten(0, (b, n))
 
     # ------------------------------------------------------------------ VAE wrappers (:665-740)
-    def encode_rgb(self, rgb_in: torch.Tensor, max_batch_size: int, verbose: bool = False, sharded: bool = False) -> torch.Tensor:
+    def encode_rgb(self, rgb_in: torch.Tensor, max_batch_size: int, verbose: bool = False, sharded: bool = False,
+                   frame_block=None, total_frames: Optional[int] = None) -> torch.Tensor:
+        """:665-704.  `sharded`: this rank encodes its block of frames and the latents are all-gathered.
+        `frame_block = (lo, hi)`: `rgb_in` holds only this rank's frames [lo, hi) of `total_frames`."""
         if 5 == rgb_in.dim():
             B, N, _, H, W = rgb_in.shape
         else:
             B, _, H, W = rgb_in.shape
             N = 1
         flat = rgb_in.reshape(B * N, *rgb_in.shape[-3:])
-        lo, hi = self.shard.block(B * N) if sharded else (0, B * N)
-        latents = []
-        for i in range(lo, hi, max_batch_size):
-            batch = flat[i:min(i + max_batch_size, hi)]
+        total = B * N if frame_block is None else int(total_frames)
+        lo, hi = self.shard.block(total) if sharded else (0, total)
+        off = 0 if frame_block is None else frame_block[0]
+        if frame_block is not None:
+            assert sharded and tuple(frame_block) == (lo, hi) and B == 1, (frame_block, lo, hi)
+        h, w = self._latent_hw(H, W)
+        if sharded:
+            buf, mine = self.shard.gather_buffer(total, (self.N_CHANNEL_PER_LATENT, h, w), self.dtype, self.device)
+        else:
+            buf = mine = torch.empty((total, self.N_CHANNEL_PER_LATENT, h, w), dtype=self.dtype, device=self.device)
+        for i, j in balanced_chunks(hi - lo, max_batch_size):
+            batch = flat[lo - off + i: lo - off + j]
             moments = self.vae.quant_conv(self.vae.encoder(batch))
             mean, _logvar = torch.chunk(moments, 2, dim=1)          # posterior mean, no sampling (Q11)
-            latents.append(mean)
-        lat = torch.cat(latents, dim=0) * self.rgb_latent_scale_factor if latents else None
-        if sharded and self.shard.world > 1:
-            h, w = self._latent_hw(H, W)
-            if lat is None:
-                lat = torch.empty((0, 4, h, w), device=self.device, dtype=self.dtype)
-            lat = self.shard.all_gather_blocks(lat, B * N)
-        return lat.unflatten(0, (B, N))
+            torch.mul(mean, self.rgb_latent_scale_factor, out=mine[i:j])
+        lat = self.shard.gather_(buf, total) if sharded else buf
+        return lat.unflatten(0, (1, total)) if frame_block is not None else lat.unflatten(0, (B, N))
 
     def _latent_hw(self, H, W):
-        with torch.no_grad():
-            f = 2 ** (len(self.vae.encoder.down_blocks) - 1)
-        return (H + f - 1) // f, (W + f - 1) // f
+        """Spatial size of the VAE latent: every encoder level but the last pads (0,1,0,1) and applies a 3x3
+        stride-2 convolution without padding (downsampling.py Downsample2D(padding=0)) = floor(size / 2)."""
+        for _ in range(len(self.vae.encoder.down_blocks) - 1):
+            H, W = H // 2, W // 2
+        return H, W
 
-    def decode_depth(self, depth_latent: torch.Tensor, max_batch_size: int, verbose: bool = False, sharded: bool = False) -> torch.Tensor:
+    def decode_depth(self, depth_latent: torch.Tensor, max_batch_size: int, verbose: bool = False, sharded: bool = False,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """:706-740.  `out` ([B, N, 1, H, W], contiguous): decode into it (no concatenation copy).
+        `sharded`: this rank decodes its block of the B*N frames and the results are all-gathered."""
         B, N, C, H, W = depth_latent.shape
         flat = depth_latent.flatten(0, 1) / self.depth_latent_scale_factor
-        lo, hi = self.shard.block(B * N) if sharded else (0, B * N)
-        outs = []
-        for i in range(lo, hi, max_batch_size):
-            batch = flat[i:min(i + max_batch_size, hi)]
-            stacked = self.vae.decoder(self.vae.post_quant_conv(batch))
-            outs.append(stacked.mean(dim=1, keepdim=True))          # mean over the 3 output channels (:737)
-        dec = torch.cat(outs, dim=0) if outs else None
-        if sharded and self.shard.world > 1:
-            if dec is None:
-                Hd, Wd = self._decoded_hw(H, W)
-                dec = torch.empty((0, 1, Hd, Wd), device=self.device, dtype=self.dtype)
-            dec = self.shard.all_gather_blocks(dec, B * N)
-        return dec.unflatten(0, (B, N))
+        Hd, Wd = self._decoded_hw(H, W)
+        if sharded:
+            assert out is None
+            lo, hi = self.shard.block(B * N)
+            buf, dst = self.shard.gather_buffer(B * N, (1, Hd, Wd), self.dtype, self.device)
+        else:
+            lo, hi = 0, B * N
+            if out is None:
+                out = torch.empty((B, N, 1, Hd, Wd), dtype=self.dtype, device=self.device)
+            assert out.is_contiguous() and tuple(out.shape) == (B, N, 1, Hd, Wd), (out.shape, (B, N, 1, Hd, Wd))
+            buf = dst = out.view(B * N, 1, Hd, Wd)
+        for i, j in balanced_chunks(hi - lo, max_batch_size):
+            stacked = self.vae.decoder(self.vae.post_quant_conv(flat[lo + i: lo + j]))
+            torch.mean(stacked, dim=1, keepdim=True, out=dst[i:j])     # mean over the 3 output channels (:737)
+        if sharded:
+            return self.shard.gather_(buf, B * N).unflatten(0, (B, N))
+        return out

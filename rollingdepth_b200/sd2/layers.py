@@ -21,6 +21,28 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+# --------------------------------------------------------------------------- config hygiene
+ANY = object()
+
+
+def check_ignored_config(kind: str, ignored: dict, implemented: dict) -> None:
+    """Constructor kwargs of a diffusers `config.json` that these modules do not take as parameters: each must have the
+    one value this implementation hard-codes (or be listed as irrelevant with `ANY`); anything else -- a key we do not
+    know, or a known key with another value -- would load with strict=True and silently compute something different,
+    so it raises instead."""
+    for k, v in ignored.items():
+        if k.startswith("_"):                       # _class_name, _diffusers_version, _name_or_path
+            continue
+        if k not in implemented:
+            raise NotImplementedError(f"{kind}: config key {k!r} (= {v!r}) is not supported by rollingdepth_b200.sd2")
+        ok = implemented[k]
+        if ok is ANY:
+            continue
+        v_cmp = tuple(v) if isinstance(v, list) else v
+        if not any(v_cmp == o for o in ok):
+            raise NotImplementedError(f"{kind}: {k} = {v!r} is not implemented (supported: {list(ok)})")
+
+
 # --------------------------------------------------------------------------- time embedding
 def timestep_embedding(timesteps: torch.Tensor, dim: int, flip_sin_to_cos: bool = True, freq_shift: float = 0.0,
                        max_period: int = 10000) -> torch.Tensor:

@@ -15,7 +15,7 @@ from typing import Dict, Optional, Sequence, Tuple, Union
 import torch
 import torch.nn as nn
 
-from .layers import (Attention, BiasConv2d, Downsample2D, GroupNormAct, ResnetBlock2D, TimestepEmbedding, Transformer2DModel, Upsample2D,
+from .layers import (ANY, check_ignored_config, Attention, BiasConv2d, Downsample2D, GroupNormAct, ResnetBlock2D, TimestepEmbedding, Transformer2DModel, Upsample2D,
                      timestep_embedding)
 
 SD2_UNET_CONFIG = dict(
@@ -93,6 +93,23 @@ class _UpBlock(nn.Module):
         return x
 
 
+# diffusers UNet2DConditionModel config keys (unet_2d_condition.py:170-224) that are not constructor parameters here,
+# with the only values this implementation covers.  `upcast_attention` is accepted either way: both reference
+# processors ignore it on their fused paths, and so does ours.
+_UNET_IGNORED_OK = dict(
+    sample_size=ANY, center_input_sample=(False,), act_fn=("silu",), norm_eps=(1e-5,), downsample_padding=(1,),
+    mid_block_type=("UNetMidBlock2DCrossAttn",), mid_block_scale_factor=(1, 1.0), mid_block_only_cross_attention=(None,),
+    only_cross_attention=(False,), dual_cross_attention=(False,), dropout=(0.0, 0), transformer_layers_per_block=(1,),
+    reverse_transformer_layers_per_block=(None,), encoder_hid_dim=(None,), encoder_hid_dim_type=(None,),
+    class_embed_type=(None,), addition_embed_type=(None,), addition_time_embed_dim=(None,), num_class_embeds=(None,),
+    upcast_attention=ANY, resnet_time_scale_shift=("default",), resnet_skip_time_act=(False,),
+    resnet_out_scale_factor=(1.0, 1), time_embedding_type=("positional",), time_embedding_dim=(None,),
+    time_embedding_act_fn=(None,), timestep_post_act=(None,), time_cond_proj_dim=(None,), conv_in_kernel=(3,),
+    conv_out_kernel=(3,), projection_class_embeddings_input_dim=(None,), attention_type=("default",),
+    class_embeddings_concat=(False,), cross_attention_norm=(None,), addition_embed_type_num_heads=ANY,
+    up_block_types=ANY, down_block_types=ANY)
+
+
 class UNet2DConditionModel(nn.Module):
     def __init__(self, in_channels=4, out_channels=4, down_block_types=SD2_UNET_CONFIG["down_block_types"],
                  up_block_types=SD2_UNET_CONFIG["up_block_types"], block_out_channels=(320, 640, 1280, 1280),
@@ -100,6 +117,7 @@ class UNet2DConditionModel(nn.Module):
                  cross_attention_dim=1280, use_linear_projection=False, norm_num_groups=32, flip_sin_to_cos=True,
                  freq_shift=0, **unused):
         super().__init__()
+        check_ignored_config("UNet2DConditionModel", unused, _UNET_IGNORED_OK)
         self.config = SimpleNamespace(
             in_channels=in_channels, out_channels=out_channels, down_block_types=tuple(down_block_types),
             up_block_types=tuple(up_block_types), block_out_channels=tuple(block_out_channels),

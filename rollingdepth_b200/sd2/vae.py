@@ -15,7 +15,7 @@ from typing import Sequence
 import torch
 import torch.nn as nn
 
-from .layers import Attention, BiasConv2d, Downsample2D, GroupNormAct, ResnetBlock2D, Upsample2D
+from .layers import ANY, Attention, BiasConv2d, check_ignored_config, Downsample2D, GroupNormAct, ResnetBlock2D, Upsample2D
 
 SD_VAE_CONFIG = dict(in_channels=3, out_channels=3, latent_channels=4, block_out_channels=(128, 256, 512, 512),
                      layers_per_block=2, norm_num_groups=32)
@@ -108,10 +108,22 @@ class Decoder(nn.Module):
         return self.conv_out(self.conv_norm_out(x))      # conv_norm_out carries the SiLU (conv_act)
 
 
+# diffusers AutoencoderKL config keys (autoencoder_kl.py:70-100) that are not constructor parameters here
+_VAE_IGNORED_OK = dict(
+    sample_size=ANY, act_fn=("silu",), down_block_types=ANY, up_block_types=ANY, force_upcast=ANY,
+    latents_mean=(None,), latents_std=(None,), shift_factor=(None,), use_quant_conv=(True,), use_post_quant_conv=(True,),
+    mid_block_add_attention=(True,))
+
+
 class AutoencoderKL(nn.Module):
     def __init__(self, in_channels=3, out_channels=3, latent_channels=4, block_out_channels=(64,), layers_per_block=1,
                  norm_num_groups=32, scaling_factor=0.18215, **unused):
         super().__init__()
+        check_ignored_config("AutoencoderKL", unused, _VAE_IGNORED_OK)
+        for key in ("down_block_types", "up_block_types"):
+            for t in unused.get(key, ()):
+                if t not in ("DownEncoderBlock2D", "UpDecoderBlock2D"):
+                    raise NotImplementedError(f"AutoencoderKL: {key} entry {t!r} is not implemented")
         self.config = SimpleNamespace(in_channels=in_channels, out_channels=out_channels, latent_channels=latent_channels,
                                       block_out_channels=tuple(block_out_channels), layers_per_block=layers_per_block,
                                       norm_num_groups=norm_num_groups, scaling_factor=scaling_factor)

@@ -1,26 +1,34 @@
 """Snippet sharding over the GPUs of one box (one process per GPU, torch.distributed / NCCL over NVLink).
 
 The reference has no parallelism at all; the units of its hot loops are independent
-(each snippet needs only the rgb latents and the shared noise), so every stage is block-partitioned over the
-ranks and only small tensors cross NVLink:
+(each snippet needs only the rgb latents and the shared noise), so every compute stage is block-partitioned over
+the ranks and results are exchanged with ONE in-place all-gather per stage into a pre-sized buffer:
 
   stage                         partition                     exchange
-  VAE encode                    frames                        all-gather rgb latents            (~6 MB, fast/150f)
-  snippet denoise + decode      snippets of each dilation     none
-  co-alignment                  snippets stay where decoded   all-reduce(min) 1 scalar; all-gather of the SUBSAMPLED
-                                                              predictions (6-77 MB); optimiser replicated (bit-identical
-                                                              on every rank) or frame-sharded with a per-iteration
-                                                              all-reduce of the per-(frame, contribution) gradient terms
-  merge                         own snippets -> per-frame     all-reduce of fp32 (sum, count) partials [N, H, W]
-                                partial sums
+  VAE encode                    frames                        all-gather rgb latents              (6 MB, fast/150 f)
+  snippet denoise + decode      snippets of each dilation     all-gather of the decoded snippets  (0.5-1.3 GB over NVLink:
+                                                              1-2 ms at the measured 600-700 GB/s)
+  co-alignment                  replicated (default): every rank holds every snippet after the gather and runs the
+                                single-GPU kernels -- global min, subsample, optimiser, merge -- so the result is
+                                bit-identical to a one-GPU run by construction and `snippet_ls` is complete on every rank;
+                                or frame-sharded optimiser ("allreduce"): each rank owns a block of frames and the
+                                per-(frame, contribution) gradient terms [N, G*w, 2] are combined by an all-reduce per
+                                iteration (rd_coalign_begin / pass / exchange / end) -- wins for long videos, where one
+                                pass costs more than the all-reduce latency
   refine                        windows of each step          all-gather of the step's predicted latents
   final decode                  frames                        all-gather
+
+Partition: rank r owns the block [r*cap, min(n, (r+1)*cap)) with cap = ceil(n / world).  The largest block is the
+same as for a balanced partition (so is the makespan), and because every block but the last ones is full, the
+all-gather of per-rank slots of `cap` rows lands every row at its global index -- no padding copies, no list of
+buffers, no concatenation.
 
 Works with any backend (`gloo` on CPU for the tests, `nccl` on GPUs).
 """
 from __future__ import annotations
 
-from typing import List, Optional, Tuple
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 
@@ -28,6 +36,7 @@ import torch
 class Shard:
     def __init__(self, rank: int = 0, world: int = 1, group=None):
         self.rank, self.world, self.group = rank, world, group
+        self._inplace_ok: Optional[bool] = None
 
     @classmethod
     def from_dist(cls, group=None) -> "Shard":
@@ -38,11 +47,18 @@ class Shard:
 
     # -------------------------------------------------------------- partition
     @staticmethod
-    def block_of(n: int, rank: int, world: int) -> Tuple[int, int]:
-        """Contiguous balanced block [lo, hi) of `n` units for `rank` (sizes differ by at most one)."""
-        base, rem = divmod(n, world)
-        lo = rank * base + min(rank, rem)
-        return lo, lo + base + (1 if rank < rem else 0)
+    def cap_of(n: int, world: int) -> int:
+        return (n + world - 1) // world if n > 0 else 0
+
+    @classmethod
+    def block_of(cls, n: int, rank: int, world: int) -> Tuple[int, int]:
+        """Contiguous block [lo, hi) of `n` units for `rank`: slots of ceil(n / world) units, the last ones short."""
+        cap = cls.cap_of(n, world)
+        lo = min(n, rank * cap)
+        return lo, min(n, lo + cap)
+
+    def cap(self, n: int) -> int:
+        return self.cap_of(n, self.world)
 
     def block(self, n: int) -> Tuple[int, int]:
         return self.block_of(n, self.rank, self.world)
@@ -64,136 +80,93 @@ class Shard:
             dist.all_reduce(t, op=ops[op], group=self.group)
         return t
 
-    def all_gather_blocks(self, local: torch.Tensor, total: int) -> torch.Tensor:
-        """Concatenate per-rank blocks (block sizes from `block_of(total, r)`) along dim 0 on every rank.
-        `local` is either this rank's block or a full-size buffer whose own block is filled in."""
-        if self.world == 1:
-            return local
-        import torch.distributed as dist
-        sizes = self.sizes(total)
-        lo, hi = self.block(total)
-        if local.shape[0] == total:
-            mine = local[lo:hi]
-        else:
-            assert local.shape[0] == hi - lo, (local.shape, lo, hi)
-            mine = local
-        mx = max(sizes)
-        pad = torch.zeros((mx, *mine.shape[1:]), dtype=mine.dtype, device=mine.device)
-        pad[: mine.shape[0]] = mine
-        bufs = [torch.empty_like(pad) for _ in range(self.world)]
-        dist.all_gather(bufs, pad, group=self.group)
-        return torch.cat([b[:s] for b, s in zip(bufs, sizes)], dim=0)
+    def gather_buffer(self, n: int, tail_shape: Sequence[int], dtype, device) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(buffer [world * cap(n), *tail], this rank's block view [hi - lo, *tail]) -- fill the view, then `gather_`."""
+        rows = max(self.world * self.cap(n), 1) if self.world > 1 else max(n, 0)
+        buf = torch.empty((rows, *tail_shape), dtype=dtype, device=device)
+        lo, hi = self.block(n)
+        return buf, buf[lo:hi]
+
+    def gather_(self, buf: torch.Tensor, n: int) -> torch.Tensor:
+        """In-place all-gather of the per-rank slots of `buf` (from `gather_buffer`); returns buf[:n] = all n rows in
+        global order on every rank."""
+        if self.world > 1 and n > 0:
+            import torch.distributed as dist
+            cap = self.cap(n)
+            mine = buf[self.rank * cap: (self.rank + 1) * cap]
+            if dist.get_backend(self.group) != "nccl":
+                mine = mine.clone()          # gloo: no aliasing guarantee for in-place all-gather
+            dist.all_gather_into_tensor(buf, mine, group=self.group)
+        return buf[:n]
 
 
-def sharded_coalign(aligner, shard: Shard, local_snips: List[torch.Tensor], dilations: List[int], seq_len: int,
-                    window: int):
-    """Multi-GPU co-alignment: `local_snips[g]` holds this rank's block of the snippets of dilation g
-    (block_of(n_g, rank)).  Returns (merged [N,1,H,W], scales, translations, history, local_snips)."""
-    import ctypes as C
+def balanced_chunks(n: int, max_chunk: int) -> List[Tuple[int, int]]:
+    """[lo, hi) ranges covering n units in ceil(n / max_chunk) chunks whose sizes differ by at most one
+    (19 -> 10 + 9 instead of 16 + 3: a tail batch of 3 runs far below the efficiency of a full one)."""
+    if n <= 0:
+        return []
+    k = (n + max_chunk - 1) // max_chunk
+    base, rem = divmod(n, k)
+    out, lo = [], 0
+    for i in range(k):
+        hi = lo + base + (1 if i < rem else 0)
+        out.append((lo, hi))
+        lo = hi
+    return out
 
+
+# ---------------------------------------------------------------------------------------------------------------
+# Frame-sharded optimiser: per-iteration all-reduce of the per-(frame, contribution) gradient terms
+# ---------------------------------------------------------------------------------------------------------------
+def coalign_optimize_allreduce(aligner, shard: Shard, pb, x_small: torch.Tensor, state: List[torch.Tensor],
+                               n_iter: int) -> torch.Tensor:
+    """depth_aligner.py:123-229 with the frames block-partitioned over the ranks: every rank
+    holds all subsampled snippets `x_small` (identical on every rank) and evaluates the fused pass for its own
+    frames; the only exchange is a sum-all-reduce of the [N, G*w, 2] gradient terms after every pass (each entry
+    is written by exactly one rank and is zero elsewhere, so the sum is exact and the parameters are bit-identical
+    to a single-GPU run).  Updates `state` in place on every rank; returns the history tensor [n_iter, 3]."""
     from . import _lib as L
-    dev = aligner.device
     lib = L.lib()
-    dt = local_snips[0].dtype
-    local = [s.to(device=dev, dtype=dt).contiguous() for s in local_snips]
-    H, W = int(local[0].shape[-2]), int(local[0].shape[-1])
-
-    # global problem (all snippets) and this rank's sub-problem view
-    pb = L.CoalignProblem()
-    pb.G, pb.w, pb.N, pb.H, pb.W = len(dilations), window, seq_len, H, W
-    pb.border, pb.factor = int(aligner.border), int(aligner.factor)
-    for g, d in enumerate(dilations):
-        pb.d[g] = int(d)
-    pb.dtype = L.dtype_code(dt)
-    L.check(lib.rd_coalign_problem_init(C.byref(pb)), "rd_coalign_problem_init")
-    blocks = [shard.block(pb.n[g]) for g in range(pb.G)]
-    for g, s in enumerate(local):
-        assert s.shape[0] == blocks[g][1] - blocks[g][0], (g, s.shape, blocks[g])
-
+    dev = x_small.device
+    hp = aligner._hparams()
+    ws_bytes = lib.rd_coalign_workspace_bytes(C.byref(pb), n_iter)
+    if ws_bytes < 0:
+        L.check(int(ws_bytes), "rd_coalign_workspace_bytes")
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     st = L.stream_ptr(dev)
-    scratch = torch.empty(lib.rd_reduce_scratch_bytes(), dtype=torch.uint8, device=dev)
-
-    # (1) global minimum: local streaming reduction + all-reduce(min) of one scalar
-    dev_min = torch.full((1,), float("inf"), dtype=torch.float32, device=dev)
-    lp = _local_problem(pb, blocks)
-    nonempty = [g for g in range(pb.G) if local[g].shape[0] > 0]
-    if nonempty:
-        sub, ptrs = _sub_problem(lp, local, nonempty)
-        L.check(lib.rd_global_min(ptrs, C.byref(sub), L.ptr(dev_min), L.ptr(scratch), st), "rd_global_min")
-    shard.all_reduce_(dev_min, "min")
-
-    # (2) subsample the local snippets, all-gather the small tensors into the global row order
-    x_small = torch.zeros((pb.n_total, pb.w, pb.P_pad), dtype=dt, device=dev)
-    if nonempty:
-        xs_local = torch.empty((sub.n_total, pb.w, pb.P_pad), dtype=dt, device=dev)
-        L.check(lib.rd_coalign_prep(ptrs, C.byref(sub), L.ptr(dev_min), L.ptr(xs_local), st), "rd_coalign_prep")
-        off = 0
-        for g in nonempty:
-            n = local[g].shape[0]
-            x_small[pb.row0[g] + blocks[g][0]: pb.row0[g] + blocks[g][1]] = xs_local[off:off + n]
-            off += n
-    shard.all_reduce_(x_small, "sum")    # rows are disjoint and zero elsewhere: x + 0 is exact, so sum == gather
-
-    # (3) optimiser replicated on every rank: identical inputs and a deterministic kernel => identical (s, t)
-    state = aligner.new_state(pb)
-    hist = aligner.optimize_state(pb, x_small, state, 0, int(aligner.num_iterations))
-
-    # (4) merge: fp32 partial (sum, count) of the local snippets, all-reduce, then round once like the reference
-    merged = _sharded_merge(aligner, shard, pb, blocks, local, dev_min, state[0], state[1])
-    scales = [state[0][pb.row0[g]: pb.row0[g] + pb.n[g]].reshape(-1, 1, 1) for g in range(pb.G)]
-    translations = [state[1][pb.row0[g]: pb.row0[g] + pb.n[g]].reshape(-1, 1, 1) for g in range(pb.G)]
-    history = [tuple(r) for r in hist.cpu().tolist()]
-    return merged, scales, translations, history, local
-
-
-def _local_problem(pb, blocks):
-    return dict(pb=pb, blocks=blocks)
-
-
-def _sub_problem(lp, local, groups):
-    """A problem struct describing only this rank's snippets (for min / prep, which are per-snippet)."""
-    import ctypes as C
-
-    from . import _lib as L
-    pb = lp["pb"]
-    sub = L.CoalignProblem()
-    C.memmove(C.byref(sub), C.byref(pb), C.sizeof(pb))
-    sub.G = len(groups)
-    row = 0
-    for i, g in enumerate(groups):
-        sub.d[i] = pb.d[g]
-        sub.n[i] = local[g].shape[0]
-        sub.row0[i] = row
-        row += local[g].shape[0]
-    for i in range(len(groups), L.RD_MAX_GROUPS):
-        sub.n[i] = 0
-        sub.row0[i] = row
-    sub.n_total = row
-    return sub, L.ptr_array([local[g] for g in groups])
-
-
-def _sharded_merge(aligner, shard, pb, blocks, local, dev_min, s, t):
-    """Per-frame partial sums over the local snippets in fp32, all-reduced; the final mean is rounded once to
-    the snippet dtype exactly like the single-GPU kernel (the fp32 sum of <= ~10 fp16 values is exact)."""
-    dev = aligner.device
-    dt = local[0].dtype
-    N, H, W, w = pb.N, pb.H, pb.W, pb.w
-    acc = torch.zeros((N, H, W), dtype=torch.float32, device=dev)
-    cnt = torch.zeros((N,), dtype=torch.float32, device=dev)
-    mn = dev_min.to(dt)
-    for g in range(pb.G):
-        lo, hi = blocks[g]
-        if hi == lo:
-            continue
-        sg = s[pb.row0[g] + lo: pb.row0[g] + hi].to(dt).view(-1, 1, 1, 1)
-        tg = t[pb.row0[g] + lo: pb.row0[g] + hi].to(dt).view(-1, 1, 1, 1)
-        y = ((local[g][:, :, 0] - mn) * sg + tg).float()            # same per-op rounding as depth_aligner.py:246-252
-        for j in range(w):
-            f0 = lo + j * pb.d[g]
-            acc[f0: f0 + (hi - lo)] += y[:, j]
-            cnt[f0: f0 + (hi - lo)] += 1
-    shard.all_reduce_(acc, "sum")
-    shard.all_reduce_(cnt, "sum")
-    merged = (acc / cnt.view(-1, 1, 1)).to(dt)[:, None].contiguous()
-    aligner.merged_minmax = torch.stack([merged.float().min(), merged.float().max()])
-    return merged
+    f_lo, f_hi = shard.block(pb.N)
+    with L.device_guard(dev):
+        L.check(lib.rd_coalign_begin(C.byref(pb), *[L.ptr(a) for a in state], n_iter, 0, L.ptr(ws), ws_bytes, st),
+                "rd_coalign_begin")
+        send, recv, nfl = C.c_void_p(), C.c_void_p(), C.c_int64()
+        for it in range(n_iter):
+            if f_hi > f_lo:
+                L.check(lib.rd_coalign_pass(L.ptr(x_small), C.byref(pb), C.byref(hp), it, 0, f_lo, f_hi, L.ptr(ws), st),
+                        "rd_coalign_pass")
+                L.count_launches(1)
+            L.check(lib.rd_coalign_exchange(C.byref(pb), L.ptr(ws), it, C.byref(send), C.byref(recv), C.byref(nfl)),
+                    "rd_coalign_exchange")
+            o_s, o_r = send.value - ws.data_ptr(), recv.value - ws.data_ptr()
+            t_send = ws[o_s: o_s + 4 * nfl.value].view(torch.float32)
+            t_recv = ws[o_r: o_r + 4 * nfl.value].view(torch.float32)
+            t_recv.copy_(t_send)
+            shard.all_reduce_(t_recv, "sum")
+        hist = torch.zeros((max(n_iter, 1), 3), dtype=torch.float32, device=dev)
+        out = [torch.zeros_like(a) for a in state]
+        if f_hi > f_lo:
+            L.check(lib.rd_coalign_end(C.byref(pb), C.byref(hp), n_iter, 0, f_lo, f_hi, *[L.ptr(a) for a in out],
+                                       L.ptr(hist), L.ptr(ws), st), "rd_coalign_end")
+            L.count_launches(2)
+        else:
+            hist[:, 1] = float("inf")
+            hist[:, 2] = float("-inf")
+    # every snippet's final state comes from the rank owning its first frame (zeros elsewhere): sum == assemble
+    packed = torch.stack(out)
+    shard.all_reduce_(packed, "sum")
+    for a, b in zip(state, packed):
+        a.copy_(b)
+    loss, mn, mx = hist[:, 0].contiguous(), hist[:, 1].contiguous(), hist[:, 2].contiguous()
+    shard.all_reduce_(loss, "sum")
+    shard.all_reduce_(mn, "min")
+    shard.all_reduce_(mx, "max")
+    return torch.stack([loss, mn, mx], dim=1)[:n_iter]

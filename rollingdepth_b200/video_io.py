@@ -38,7 +38,11 @@ def resize_max_res(img: torch.Tensor, max_edge_resolution: int, resample_method:
 def _iter_frames_rgb(input_path):
     try:
         import av  # type: ignore
-        container = av.open(input_path)
+        av_open = av.open
+    except (ImportError, AttributeError):
+        av_open = None
+    if av_open is not None:
+        container = av_open(input_path)
         stream = container.streams.video[0]
         stream.thread_type = "AUTO"
         try:
@@ -47,8 +51,6 @@ def _iter_frames_rgb(input_path):
         finally:
             container.close()
         return
-    except ImportError:
-        pass
     import cv2  # OpenCV fallback decoder (same frames, BGR -> RGB)
     cap = cv2.VideoCapture(str(input_path))
     if not cap.isOpened():

@@ -39,3 +39,12 @@ def deterministic_init_(module: torch.nn.Module, seed: int = 0, gain: float = 1.
             v = torch.randn(p.shape, generator=g) * (gain / fan_in ** 0.5)
         p.copy_(v.to(p.dtype))
     return module
+
+
+def synth_video(n, h, w, seed=0):
+    """Smooth synthetic clip in [-1, 1], float32 [1, n, 3, h, w] (same generator as bench.py's `synth_video`)."""
+    g = torch.Generator().manual_seed(seed)
+    low = torch.rand(n, 3, h // 16 + 2, w // 16 + 2, generator=g)
+    vid = torch.nn.functional.interpolate(low, size=(h, w), mode="bilinear", align_corners=False)
+    drift = torch.linspace(0, 1, n)[:, None, None, None] * 0.2
+    return ((vid + drift).clamp(0, 1) * 2 - 1)[None].contiguous()

@@ -67,15 +67,50 @@ def test_problem_init_and_argument_checks():
     assert L.lib().rd_coalign_problem_init(C.byref(pb)) == -1   # dilation too large for the clip
 
 
-def test_block_partition_is_balanced_and_contiguous():
+def test_block_partition_is_contiguous_with_minimal_makespan():
+    """Slots of ceil(n / world) units: contiguous, complete, the largest block as small as a balanced partition's,
+    and every rank's block starts at rank * cap -- which is what lets one in-place all-gather assemble the result."""
     from rollingdepth_b200.sharding import Shard
-    for n in (0, 1, 7, 100, 148, 378):
+    for n in (0, 1, 7, 9, 100, 148, 248, 378):
         for world in (1, 2, 3, 4, 8):
             blocks = [Shard.block_of(n, r, world) for r in range(world)]
             assert blocks[0][0] == 0 and blocks[-1][1] == n
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in blocks]
-            assert max(sizes) - min(sizes) <= 1
+            cap = Shard.cap_of(n, world)
+            assert max(sizes) == cap == -(-n // world)
+            assert all(a == min(n, r * cap) for r, (a, _) in enumerate(blocks))
+    assert Shard.block_of(248, 3, 8) == (93, 124)      # the `fast` preset's 148 + 100 snippets: 31 per rank, no remainder
+
+
+def test_balanced_chunks():
+    from rollingdepth_b200.sharding import balanced_chunks
+    assert balanced_chunks(19, 16) == [(0, 10), (10, 19)]           # not 16 + 3
+    assert balanced_chunks(57, 36) == [(0, 29), (29, 57)]
+    assert balanced_chunks(16, 16) == [(0, 16)] and balanced_chunks(0, 16) == []
+    for n in range(1, 80):
+        for m in (1, 3, 16, 36):
+            ch = balanced_chunks(n, m)
+            assert ch[0][0] == 0 and ch[-1][1] == n and all(a[1] == b[0] for a, b in zip(ch, ch[1:]))
+            sizes = [b - a for a, b in ch]
+            assert max(sizes) <= m and max(sizes) - min(sizes) <= 1 and len(ch) == -(-n // m)
+
+
+def test_product_snippet_scheduler_matches_reference(golden_dir):
+    """The PRODUCT copy of get_snippet_indice / cap_max_dilation (rollingdepth_pipeline.py:465-515) against all
+    reference-generated cases (integer work: exact)."""
+    import json
+    from rollingdepth_b200.pipeline import RollingDepthPipeline as P
+    cases = json.load(open(os.path.join(golden_dir, "snippets.json")))
+    assert len(cases) >= 96
+    for c in cases:
+        if c["kind"] == "init":
+            capped = P.cap_max_dilation(seq_len=c["seq_len"], snippet_len=c["snippet_len"], dilation=c["dilation"], verbose=False)
+            assert capped == c["capped"], c
+            idx = P.get_snippet_indice(0, [999], c["seq_len"], c["snippet_len"], capped, capped, 1)
+        else:
+            idx = P.get_snippet_indice(c["i_step"], list(range(c["total"])), c["seq_len"], 3, c["start"], 1, 1)
+        assert idx == c["idx"], c
 
 
 _WORKER = r'''
@@ -85,35 +120,40 @@ from rollingdepth_b200.sharding import Shard
 from oracle import schedule as osch
 dist.init_process_group("gloo")
 sh = Shard.from_dist()
-# (1) uneven block all-gather reproduces the full tensor in rank order
-total = 7
-full = torch.arange(total * 3, dtype=torch.float32).reshape(total, 3)
-lo, hi = sh.block(total)
-got = sh.all_gather_blocks(full[lo:hi].clone(), total)
-assert torch.equal(got, full), (got, full)
-buf = torch.zeros_like(full); buf[lo:hi] = full[lo:hi]
-assert torch.equal(sh.all_gather_blocks(buf, total), full)
-# (2) snippet-sharded "denoise": every rank processes its block of snippets, results are identical to 1 rank
-N, n, d = 30, 3, 4
-idx = osch.get_snippet_indice(0, 1, N, n, d, d, 1)
+# (1) in-place all-gather of per-rank slots reproduces the full tensor in global order (uneven and empty blocks)
+for total in (7, 1, 8):
+    full = torch.arange(total * 3, dtype=torch.float32).reshape(total, 3)
+    lo, hi = sh.block(total)
+    buf, mine = sh.gather_buffer(total, (3,), torch.float32, "cpu")
+    assert buf.shape[0] == sh.world * sh.cap(total) and mine.shape[0] == hi - lo
+    mine.copy_(full[lo:hi])
+    got = sh.gather_(buf, total)
+    assert torch.equal(got, full), (got, full)
+# (2) snippet-sharded "denoise" over the flattened (dilation, snippet) list: identical to 1 rank
+N, n = 30, 3
+flat = []
+for d in (1, 4):
+    flat += osch.get_snippet_indice(0, 1, N, n, d, d, 1)
 frames = torch.arange(N, dtype=torch.float32)
-def work(ix): return torch.stack([frames[i].sum() * 2 + 1 for i in map(torch.tensor, ix)])
-lo, hi = sh.block(len(idx))
-mine = work(idx[lo:hi])
-allr = sh.all_gather_blocks(mine, len(idx))
-assert torch.equal(allr, work(idx))
-# (3) per-frame partial sums of the merge: all-reduce(sum) equals the single-rank sums
-acc = torch.zeros(N); cnt = torch.zeros(N)
+def work(ix): return torch.stack([frames[i].sum() * 2 + 1 for i in map(torch.tensor, ix)]) if ix else torch.zeros(0)
+lo, hi = sh.block(len(flat))
+buf, mine = sh.gather_buffer(len(flat), (), torch.float32, "cpu")
+mine.copy_(work(flat[lo:hi]))
+assert torch.equal(sh.gather_(buf, len(flat)), work(flat))
+# (3) sum / min / max all-reduce and broadcast
+acc = torch.zeros(N)
 for k in range(lo, hi):
-    for j, f in enumerate(idx[k]):
-        acc[f] += float(k + j); cnt[f] += 1
-sh.all_reduce_(acc); sh.all_reduce_(cnt)
-ref_a = torch.zeros(N); ref_c = torch.zeros(N)
-for k in range(len(idx)):
-    for j, f in enumerate(idx[k]):
-        ref_a[f] += float(k + j); ref_c[f] += 1
-assert torch.equal(acc, ref_a) and torch.equal(cnt, ref_c)
+    for j, f in enumerate(flat[k]):
+        acc[f] += float(k + j)
+sh.all_reduce_(acc)
+ref_a = torch.zeros(N)
+for k in range(len(flat)):
+    for j, f in enumerate(flat[k]):
+        ref_a[f] += float(k + j)
+assert torch.equal(acc, ref_a)
 mn = torch.tensor([float(sh.rank + 3)]); sh.all_reduce_(mn, "min"); assert float(mn) == 3.0
+mx = torch.tensor([float(sh.rank + 3)]); sh.all_reduce_(mx, "max"); assert float(mx) == 2.0 + sh.world
+b = torch.full((2,), float(sh.rank)); sh.broadcast_(b); assert float(b.sum()) == 0.0
 dist.destroy_process_group()
 print("rank", sh.rank, "ok")
 '''

@@ -103,6 +103,60 @@ def test_xattn_full_size_level0_fast_preset(dtype):
     assert err <= 2e-2, f"max-abs {err}"
 
 
+def _sampled_rows_ref(q, k, v, b, h, rows):
+    """fp32 softmax(q k^T / sqrt(D)) v for a few query rows of one (batch, head) -- exact reference for shapes whose
+    full score matrix would not be worth computing."""
+    qs = q[b, rows, h].float()                                   # [r, D]
+    s = (qs @ k[b, :, h].float().T) * (q.shape[-1] ** -0.5)      # [r, Sk]
+    return torch.softmax(s, dim=-1) @ v[b, :, h].float()
+
+
+@pytest.mark.parametrize("B,S,H,what", [
+    (16, 15552, 5, "fast preset level 0 at the snippet batch the pipeline runs (auto-selects the three-tile kernel)"),
+    (4, 27648, 5, "full preset level 0, many-wave grid (three-tile kernel)"),
+    (16, 3888, 10, "fast preset level 1 at B = 16"),
+    (1, 131072, 5, "largest shape of the config-5 sweep: n = 8 frames of 1024x1024"),
+    (1, 49152, 5, "n = 3 frames of 1024x1024"),
+])
+def test_xattn_production_shapes_default_flags(B, S, H, what):
+    """flags = 0 (the kernel selection the product path uses) at the shapes the bench runs, checked on sampled
+    (batch, head, row) triples against an fp32 softmax over all keys."""
+    from rollingdepth_b200 import ops
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(S + B)
+    q, k, v = [torch.randn(B, S, H * 64, device=dev, dtype=torch.float16, generator=g).view(B, S, H, 64) for _ in range(3)]
+    out = ops.xattn_fwd(q, k, v, flags=0)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
+    worst = 0.0
+    rows = torch.tensor([0, 1, 127, 128, 383, 384, 385, S // 2, S - 385, S - 129, S - 2, S - 1], device=dev)
+    for b in sorted({0, B // 2, B - 1}):
+        for h in sorted({0, H // 2, H - 1}):
+            ref = _sampled_rows_ref(q, k, v, b, h, rows)
+            worst = max(worst, float((out[b, rows, h].float() - ref).abs().max()))
+    assert worst <= 2e-2, f"{what}: max-abs {worst}"
+    # every query tile was written: no row of the (poisoned) output may be left untouched
+    out2 = torch.full_like(out, float("nan"))
+    ops.xattn_fwd(q, k, v, out=out2, flags=0)
+    assert torch.isfinite(out2.float()).all()
+    assert torch.equal(out, out2), "the kernel must be deterministic run to run"
+
+
+def test_xattn_fp32_processor_shape_level0():
+    """fp32 path (`paper` preset / cfg1) at S = 15552, 5 heads: <= 1e-4 max-abs against a float64 softmax on sampled rows."""
+    from rollingdepth_b200 import ops
+    dev = _dev()
+    S, H = 15552, 5
+    g = torch.Generator(device=dev).manual_seed(7)
+    q, k, v = [torch.randn(1, S, H * 64, device=dev, dtype=torch.float32, generator=g).view(1, S, H, 64) for _ in range(3)]
+    out = ops.xattn_fwd(q, k, v)
+    rows = torch.tensor([0, 77, 5000, S - 1], device=dev)
+    for h in (0, 4):
+        s = (q[0, rows, h].double() @ k[0, :, h].double().T) * 0.125
+        ref = torch.softmax(s, dim=-1) @ v[0, :, h].double()
+        assert float((out[0, rows, h].double() - ref).abs().max()) <= 1e-4
+
+
 def test_xattn_head_major_strides_and_scale():
     from rollingdepth_b200 import ops
     dev = _dev()

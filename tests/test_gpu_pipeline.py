@@ -67,6 +67,93 @@ def test_pipeline_fp32_matches_reference_fixture(golden_dir, tag, dil, refine, s
     assert _absrel(res.depth_pred, dp) <= 1e-3      # north star: final depth AbsRel difference <= 1e-3
 
 
+def _full_models(dev, dtype, gain=0.7):
+    """Full SD2-architecture UNet (866 M) + SD VAE (84 M) with the name-keyed init of the cfg1 fixture."""
+    from rollingdepth_b200.sd2.unet import UNet2DConditionModel
+    from rollingdepth_b200.sd2.vae import AutoencoderKL
+    unet = mu.deterministic_init_(UNet2DConditionModel(**mu.SD2_UNET).eval(), seed=11, gain=gain)
+    vae = mu.deterministic_init_(AutoencoderKL(**{k: v for k, v in mu.SD_VAE.items() if not k.endswith("block_types")}).eval(),
+                                 seed=12, gain=gain)
+    return unet.to(dev, dtype), vae.to(dev, dtype)
+
+
+def test_cfg1_fp32_matches_reference_run(golden_dir):
+    """BASELINE.json configs[0]: 16 frames 256x256, dilations [1, 4], 1 denoise step, 2000 co-alignment iterations,
+    full SD2 architecture, fp32 -- the product pipeline on the GPU against the output of the REFERENCE pipeline run
+    on CPU in the build container (oracle/gen_golden_cfg1.py -> tests/golden/cfg1_reference.npz).
+    Tolerances: decoded snippets 2e-4 max-abs; final depth AbsRel <= 1e-3 (north star); the reference's own
+    sensitivity floor (same aligner, snippets perturbed by 1e-7) is stored in the fixture and printed beside it."""
+    from rollingdepth_b200.pipeline import RollingDepthPipeline
+    from rollingdepth_b200.scheduler import DDIMSchedule
+    dev = _dev()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = np.load(os.path.join(golden_dir, "cfg1_reference.npz"))
+    frames = mu.synth_video(16, 256, 256, seed=0)
+    assert abs(float(frames.double().sum()) - float(g["frames_checksum"])) < 1e-3 * abs(float(g["frames_checksum"])) + 1.0
+    unet, vae = _full_models(dev, torch.float32)
+    pipe = RollingDepthPipeline(unet, vae, DDIMSchedule(**mu.DDIM_CFG))
+    pipe.empty_text_embed = torch.from_numpy(g["text"]).to(dev)
+    res = pipe.forward(input_frames=frames, dilations=[1, 4], cap_dilation=True, snippet_lengths=[3], init_infer_steps=[1],
+                       strides=[1], coalign_kwargs=None, refine_step=0, refine_snippet_len=3, refine_start_dilation=6,
+                       generator=torch.Generator().manual_seed(0), verbose=False, max_vae_bs=4, unload_snippet=False)
+    worst = 0.0
+    for gi in range(2):
+        assert tuple(res.snippet_ls[gi].shape) == tuple(g[f"snip{gi}_shape"])
+        for key in [k for k in g.files if k.startswith(f"snip{gi}_") and not k.endswith("shape")]:
+            r = int(key.split("_")[1])
+            ref = torch.from_numpy(g[key])
+            worst = max(worst, float((res.snippet_ls[gi][r, :, :, ::2, ::2] - ref).abs().max()) / max(1.0, float(ref.abs().max())))
+    ref_depth = torch.from_numpy(g["depth_pred"])
+    ar = _absrel(res.depth_pred, ref_depth)
+    scales, trans, hist = pipe.last_alignment
+    ds = max(float((scales[i].flatten().cpu() - torch.from_numpy(g[f"scale{i}"])).abs().max()) for i in range(2))
+    loss_rel = abs(hist[-1][0] - float(g["hist"][-1][0])) / abs(float(g["hist"][-1][0]))
+    print(f"cfg1: snippets max-abs (rel. to range) {worst:.2e}; depth AbsRel {ar:.2e} (reference's own floor "
+          f"{float(g['floor_absrel']):.2e}); scale max-abs diff {ds:.2e} (floor rel {float(g['floor_scale_rel']):.2e}); "
+          f"final loss rel diff {loss_rel:.2e}")
+    assert worst < 2e-4
+    assert res.depth_pred.shape == ref_depth.shape and torch.equal(res.depth_pred, res.depth_coaligned)
+    assert ar <= 1e-3
+    assert loss_rel <= 1e-3
+    assert len(hist) == 2000
+
+
+@pytest.mark.parametrize("H,W,dil", [(432, 768, [1, 10]), (576, 1024, [1, 10])])
+def test_real_size_fp16_matches_oracle_on_device(H, W, dil):
+    """fp16 at the presets' real resolutions (30 frames of 768x432 / 1024x576, full SD2 architecture, level-0 attention
+    at S = 15552 / 27648 through the three-tile tcgen05 kernel at B = 16): product pipeline against the oracle's
+    op-for-op restatement (one snippet per UNet call, torch SDPA, eager aligner) on the same device.
+    fp16 floor: both sides round every activation to 11 bits, so they agree to a few 1e-3 AbsRel, not 1e-5."""
+    from rollingdepth_b200.pipeline import RollingDepthPipeline
+    from rollingdepth_b200.scheduler import DDIMSchedule
+    from rollingdepth_b200.sd2.layers import TorchSDPAProcessor
+    dev = _dev()
+    n = 30
+    unet, vae = _full_models(dev, torch.float16)
+    frames = mu.synth_video(n, H, W, seed=1)
+    text = torch.randn(1, 2, 1024, generator=torch.Generator().manual_seed(2)).to(dev).half()
+    pipe = RollingDepthPipeline(unet, vae, DDIMSchedule(**mu.DDIM_CFG), snippet_batch=16)
+    pipe.empty_text_embed = text
+    kw = dict(coalign_kwargs=dict(num_iterations=100), refine_step=0)
+    res = pipe.forward(input_frames=frames, dilations=list(dil), cap_dilation=True, snippet_lengths=[3], init_infer_steps=[1],
+                       strides=[1], refine_snippet_len=3, refine_start_dilation=6,
+                       generator=torch.Generator(device=dev).manual_seed(0), verbose=False, max_vae_bs=12, unload_snippet=False, **kw)
+    unet.set_attn_processor(TorchSDPAProcessor())
+    for m in list(unet.modules()) + list(vae.modules()):
+        if hasattr(m, "fused"):
+            m.fused = False                     # the oracle runs the plain torch modules (F.group_norm, eager adds)
+    ora = opipe.forward(unet, vae, mu.DDIM_CFG, text, frames, list(dil), cap_dilation=True, max_vae_bs=4,
+                        generator=torch.Generator(device=dev).manual_seed(0), **kw)
+    assert torch.isfinite(res.depth_pred.float()).all()
+    rng = max(float(s.float().abs().max()) for s in ora.snippet_ls)
+    err = max(float((a.float() - b.float().cpu()).abs().max()) for a, b in zip(res.snippet_ls, ora.snippet_ls))
+    ar = _absrel(res.depth_pred, ora.depth_pred.cpu())
+    print(f"{W}x{H} fp16: snippet max-abs {err:.3e} (range {rng:.2f}), depth AbsRel vs oracle {ar:.2e}")
+    assert err <= 2e-2 * max(1.0, rng)
+    assert ar <= 3e-3
+
+
 def test_pipeline_fp16_matches_oracle_on_device():
     """fp16: product pipeline (tcgen05 attention, fused DDIM/aligner kernels, batched snippets) against the
     oracle's op-for-op restatement run with library attention on the same GPU."""

@@ -97,3 +97,17 @@ def test_oracle_pipeline_matches_reference(gold, tag, kw):
     d0, d1 = (res.depth_pred + 1) / 2, (dp + 1) / 2
     absrel = float(((d0 - d1).abs() / d1.clamp_min(1e-3)).mean())
     assert absrel <= 1e-3, absrel
+
+
+def test_unsupported_config_values_are_refused():
+    """A diffusers config.json key these modules do not implement must raise instead of loading with strict=True and
+    silently computing something else (only the values the SD2 / RollingDepth checkpoints use are accepted)."""
+    with torch.device("meta"):
+        UNet2DConditionModel(**mu.SD2_UNET, upcast_attention=True, sample_size=96, act_fn="silu", _class_name="UNet2DConditionModel")
+        AutoencoderKL(**mu.SD_VAE, sample_size=768, force_upcast=True)
+        for bad in (dict(only_cross_attention=True), dict(resnet_time_scale_shift="scale_shift"), dict(norm_eps=1e-6),
+                    dict(transformer_layers_per_block=2), dict(class_embed_type="timestep"), dict(not_a_key=1)):
+            with pytest.raises(NotImplementedError):
+                UNet2DConditionModel(**mu.SD2_UNET, **bad)
+        with pytest.raises(NotImplementedError):
+            AutoencoderKL(**{k: v for k, v in mu.SD_VAE.items() if not k.endswith("block_types")}, mid_block_add_attention=False)
