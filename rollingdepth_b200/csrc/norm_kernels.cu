@@ -5,7 +5,8 @@
 // autoencoders/vae.py:284-347).  cuDNN's Blackwell convolutions want NHWC; torch's group_norm then
 // falls back to NCHW round-trip copies.  These two kernels keep everything NHWC:
 //   stats : one coalesced pass, per-channel shifted sums in registers -> per-(sample, chunk, group)
-//           partials in double (deterministic: no float atomics);
+//           partials in double.  No atomics of any kind: the row-threads of a channel are combined through
+//           shared memory in a fixed order, so two launches on the same input give the same bits;
 //   apply : y = silu(round_T(x * a_c + b_c)), a_c = rstd_g * gamma_c, b_c = beta_c - mean_g * a_c,
 //           16-byte vectors, the group statistics are reduced from the partials in the prologue.
 // Algorithmic traffic: 2 reads + 1 write of the activation.
@@ -51,9 +52,12 @@ __device__ __forceinline__ void gn_unpack(const uint4& u, float* f) {
 template <typename T>
 __global__ void __launch_bounds__(kGnMaxThreads) gn_stats_kernel(const GnParams p) {
     constexpr int VN = GnVec<T>::N;
-    extern __shared__ double sh_d[];                  // [2][Cs] channel sums (double)
+    extern __shared__ double sh_d[];                  // [2][Cs] channel sums (double), then float [2][R][Cs] + [Cs]
     double* ch_sum = sh_d;
     double* ch_sq = sh_d + p.Cs;
+    float* st1 = reinterpret_cast<float*>(sh_d + 2 * p.Cs);   // [R][Cs] shifted sums per row-thread
+    float* st2 = st1 + (size_t)p.R * p.Cs;                     // [R][Cs] shifted sums of squares
+    float* stK = st2 + (size_t)p.R * p.Cs;                     // [Cs]    the shift of each channel
     const int n = blockIdx.y, chunk = blockIdx.x;
     const int c_off = blockIdx.z * p.Cs;
     const int cv = threadIdx.x % p.CV, r = threadIdx.x / p.CV;
@@ -61,9 +65,6 @@ __global__ void __launch_bounds__(kGnMaxThreads) gn_stats_kernel(const GnParams 
     const T* xs = reinterpret_cast<const T*>(p.x) + (size_t)n * p.HW * p.C + c_off;
     const int row0 = chunk * p.rows_per_chunk;
     const int row1 = min(p.HW, row0 + p.rows_per_chunk);
-
-    for (int c = threadIdx.x; c < 2 * p.Cs; c += blockDim.x) sh_d[c] = 0.0;
-    __syncthreads();
 
     float shift[VN], s1[VN], s2[VN], pre[VN];
     if (active) {
@@ -102,20 +103,36 @@ __global__ void __launch_bounds__(kGnMaxThreads) gn_stats_kernel(const GnParams 
                 s2[i] = fmaf(da, da, s2[i]);
             }
         }
-        // un-shift in double and combine the R row-threads of each channel
-        const int first = row0 + r;
-        const double nn = first < row1 ? (double)((row1 - first + p.R - 1) / p.R) : 0.0;
+        // park the per-thread shifted sums; the row-threads of a channel are combined below in the order r = 0..R-1
+        float* d1 = st1 + (size_t)r * p.Cs + cv * VN;
+        float* d2 = st2 + (size_t)r * p.Cs + cv * VN;
 #pragma unroll
-        for (int i = 0; i < VN; ++i) {
-            const double K = (double)shift[i], d1 = (double)s1[i], d2 = (double)s2[i];
-            atomicAdd(&ch_sum[cv * VN + i], d1 + nn * K);
-            atomicAdd(&ch_sq[cv * VN + i], d2 + 2.0 * K * d1 + nn * K * K);
+        for (int i = 0; i < VN; i += 4) {
+            *reinterpret_cast<float4*>(d1 + i) = make_float4(s1[i], s1[i + 1], s1[i + 2], s1[i + 3]);
+            *reinterpret_cast<float4*>(d2 + i) = make_float4(s2[i], s2[i + 1], s2[i + 2], s2[i + 3]);
+        }
+        if (r == 0) {
+#pragma unroll
+            for (int i = 0; i < VN; ++i) stK[cv * VN + i] = shift[i];
         }
     }
     __syncthreads();
-    // channels -> groups (fixed order => deterministic up to the shared-memory atomics above, which add
-    // at most R <= 32 doubles per address; double addition of these magnitudes is order-insensitive to
-    // ~1e-16 relative, far below the fp16/fp32 output rounding)
+    // un-shift in double and combine the R row-threads of each channel (fixed order => bit-reproducible)
+    for (int c = threadIdx.x; c < p.Cs; c += blockDim.x) {
+        const double K = (double)stK[c];
+        double a = 0.0, b = 0.0;
+        for (int rr = 0; rr < p.R; ++rr) {
+            const int first = row0 + rr;
+            const double nn = first < row1 ? (double)((row1 - first + p.R - 1) / p.R) : 0.0;
+            const double d1 = (double)st1[(size_t)rr * p.Cs + c], d2 = (double)st2[(size_t)rr * p.Cs + c];
+            a += d1 + nn * K;
+            b += d2 + 2.0 * K * d1 + nn * K * K;
+        }
+        ch_sum[c] = a;
+        ch_sq[c] = b;
+    }
+    __syncthreads();
+    // channels -> groups (fixed order)
     const int Gs = p.Cs / p.cpg, g0 = c_off / p.cpg;
     for (int g = threadIdx.x; g < Gs; g += blockDim.x) {
         double a = 0.0, b = 0.0;
@@ -358,7 +375,17 @@ int rd_groupnorm_nhwc(const void* x, void* y, const void* gamma, const void* bet
     cudaStream_t st = (cudaStream_t)stream;
     const int threads = p.CV * p.R;
     dim3 grid(p.chunks, N, C / p.Cs);
-    const size_t sm_stats = 2 * (size_t)p.Cs * sizeof(double), sm_apply = 2 * (size_t)p.Cs * sizeof(float);
+    const size_t sm_stats = 2 * (size_t)p.Cs * sizeof(double) + (2 * (size_t)p.R + 1) * p.Cs * sizeof(float);
+    const size_t sm_apply = 2 * (size_t)p.Cs * sizeof(float);
+    {   // up to 16 B * Cs + 8 B * R * Cs = 96 KB for the widest slice: opt in above the 48 KB default (per device)
+        static PerDeviceOnce configured;
+        if (configured.needed()) {
+            RD_CUDA(cudaFuncSetAttribute(gn_stats_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            RD_CUDA(cudaFuncSetAttribute(gn_stats_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            RD_CUDA(cudaFuncSetAttribute(gn_stats_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            configured.done();
+        }
+    }
     switch (dtype) {
         case RD_F32:
             gn_stats_kernel<float><<<grid, threads, sm_stats, st>>>(p);

@@ -198,8 +198,7 @@ def test_output_modes_agree_and_results_are_fresh_by_default(golden_dir):
     pipe.output_mode = "pinned_views"
     c = _run(pipe, frames, [1, 3], 0, torch.Generator().manual_seed(0))
     assert c.depth_pred.is_pinned()
-    # two separate forward passes: equal up to the order of the shared-memory double atomics in the GroupNorm statistics
-    close = lambda x, y: float((x - y).abs().max()) <= 1e-4
-    assert close(c.depth_pred, a.depth_pred) and close(c.depth_coaligned, a.depth_coaligned)
+    # two separate forward passes of the same input: every kernel of the path is deterministic (no float atomics)
+    assert torch.equal(c.depth_pred, a.depth_pred) and torch.equal(c.depth_coaligned, a.depth_coaligned)
     for x, y in zip(c.snippet_ls, a.snippet_ls):
-        assert close(x, y)
+        assert torch.equal(x, y)

@@ -44,6 +44,10 @@ def time_cuda(fn, warmup=3, iters=10, flush=None):
 
 
 def bench_attn(args):
+    """Cross-frame attention: the preset shapes at B = 1 and at the snippet batch the pipeline runs (B = 16 / 4), and with
+    --full the config-5 sweep (n = 3..8 frames x 512 / 768 / 1024 px, levels 0 and 1, B = 1).  Comparator on the same
+    strided views: torch SDPA (the reference's call) -- default backend choice and, explicitly, cuDNN and flash."""
+    from torch.nn.attention import SDPBackend, sdpa_kernel
     from rollingdepth_b200 import ops
     dev = torch.device("cuda:0")
     hbm, tf_peak, src = peaks()
@@ -51,34 +55,44 @@ def bench_attn(args):
     cases = []
     if args.full:
         for res in (512, 768, 1024):
-            for n in (3, 4, 6, 8):
+            for n in (3, 4, 5, 6, 7, 8):
                 hw = (res // 8) ** 2
-                cases.append((f"{res}px n={n} L0", n * hw, 5))
-                cases.append((f"{res}px n={n} L1", n * hw // 4, 10))
-    cases += [("fast L0 (768x432 n=3)", 15552, 5), ("fast L1", 3888, 10), ("fast L2", 1008, 20), ("fast mid", 252, 20),
-              ("full L0 (1024x576 n=3)", 27648, 5), ("full L1", 6912, 10)]
+                cases.append((f"{res}px n={n} L0", 1, n * hw, 5))
+                cases.append((f"{res}px n={n} L1", 1, n * hw // 4, 10))
+    cases += [("fast L0 (768x432 n=3)", 1, 15552, 5), ("fast L1", 1, 3888, 10), ("fast L2", 1, 1008, 20), ("fast mid", 1, 252, 20),
+              ("full L0 (1024x576 n=3)", 1, 27648, 5), ("full L1", 1, 6912, 10),
+              ("fast L0 B=16", 16, 15552, 5), ("fast L1 B=16", 16, 3888, 10), ("fast L2 B=16", 16, 1008, 20),
+              ("full L0 B=16", 16, 27648, 5), ("full L1 B=16", 16, 6912, 10), ("full L0 B=4", 4, 27648, 5)]
     if args.only:
         cases = [c for c in cases if args.only in c[0]]
-    for dtype in ((torch.float16,) if args.only else (torch.float16, torch.bfloat16)):
-        for name, S, H in cases:
-            q = torch.randn(1, S, H * 64, device=dev, dtype=dtype).view(1, S, H, 64)
-            k = torch.randn(1, S, H * 64, device=dev, dtype=dtype).view(1, S, H, 64)
-            v = torch.randn(1, S, H * 64, device=dev, dtype=dtype).view(1, S, H, 64)
+    backends = [("torch_sdpa", None), ("cudnn", SDPBackend.CUDNN_ATTENTION), ("flash", SDPBackend.FLASH_ATTENTION)]
+    for dtype in ((torch.float16,) if (args.only or args.full) else (torch.float16, torch.bfloat16)):
+        for name, B, S, H in cases:
+            q, k, v = [torch.randn(B, S, H * 64, device=dev, dtype=dtype).view(B, S, H, 64) for _ in range(3)]
             out = torch.empty_like(q)
-            flops = 4.0 * H * S * S * 64
+            flops = 4.0 * B * H * S * S * 64
+            iters = 10 if flops < 3e13 else 5
             for flags in args.flags:
-                med, best = time_cuda(lambda: ops.xattn_fwd(q, k, v, out=out, flags=flags), flush=flush)
-                rec = dict(bench="xattn", case=name, S=S, H=H, dtype=str(dtype), flags=flags, ms=med, ms_best=best,
+                med, best = time_cuda(lambda: ops.xattn_fwd(q, k, v, out=out, flags=flags), iters=iters, flush=flush)
+                rec = dict(bench="xattn", case=name, B=B, S=S, H=H, dtype=str(dtype), flags=flags, ms=med, ms_best=best,
                            tflops=flops / med / 1e9, frac_of_peak=flops / med / 1e9 / tf_peak, peak=tf_peak, peak_src=src)
-                # comparator: torch SDPA (what the reference calls) on the same strided views
-                if flags == args.flags[0]:
+                if flags == args.flags[0] and not args.no_sdpa:
                     qt, kt, vt = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
-                    try:
-                        m2, _ = time_cuda(lambda: torch.nn.functional.scaled_dot_product_attention(qt, kt, vt), flush=flush)
-                        rec["torch_sdpa_ms"] = m2
-                        rec["torch_sdpa_tflops"] = flops / m2 / 1e9
-                    except Exception as e:  # noqa: BLE001
-                        rec["torch_sdpa_err"] = str(e)[:80]
+                    for bname, be in backends:
+                        try:
+                            if be is None:
+                                m2, _ = time_cuda(lambda: torch.nn.functional.scaled_dot_product_attention(qt, kt, vt),
+                                                  iters=iters, flush=flush)
+                            else:
+                                with sdpa_kernel(be):
+                                    m2, _ = time_cuda(lambda: torch.nn.functional.scaled_dot_product_attention(qt, kt, vt),
+                                                      iters=iters, flush=flush)
+                            rec[f"{bname}_ms"] = m2
+                            rec[f"{bname}_tflops"] = flops / m2 / 1e9
+                        except Exception as e:  # noqa: BLE001
+                            rec[f"{bname}_err"] = str(e)[:80]
+                    best_lib = max([rec.get(f"{b}_tflops", 0.0) for b, _ in backends])
+                    rec["vs_best_library"] = rec["tflops"] / best_lib if best_lib > 0 else None
                 print(json.dumps(rec), flush=True)
 
 
@@ -172,5 +186,6 @@ if __name__ == "__main__":
     ap.add_argument("--iters", type=int, default=200)
     ap.add_argument("--flags", type=int, nargs="+", default=[0])
     ap.add_argument("--only", default="")
+    ap.add_argument("--no-sdpa", action="store_true", help="skip the torch SDPA comparators")
     a = ap.parse_args()
     {"attn": bench_attn, "align": bench_align, "gn": bench_gn}[a.what](a)
