@@ -824,6 +824,19 @@ static int pass_cfg(const rd_coalign_problem* p) {
 }
 static int pass_smem_budget(const rd_coalign_problem* p) { return pass_cfg(p) == 1 ? 65536 : 98304; }
 
+// Chunks per frame beyond what shared memory requires.  With one CTA per frame a 150-frame clip is 150 CTAs of 6 warps
+// on 148 SMs: every SM runs latency-bound at 1.5 warps per scheduler, and two SMs run two frames.  Splitting frames
+// into chunks trades that for the cross-chunk ticket; RD_COALIGN_CHUNKS forces a count (A/B measurements).
+static int pass_min_chunks(const rd_coalign_problem* p) {
+    static int forced = -2;
+    if (forced == -2) {
+        const char* e = getenv("RD_COALIGN_CHUNKS");
+        forced = e ? atoi(e) : -1;
+    }
+    if (forced >= 1) return forced;
+    return 1;
+}
+
 static WsLayout ws_layout(const rd_coalign_problem* p, int n_iter) {
     WsLayout L{};
     const int R = p->G * p->w;
@@ -837,7 +850,11 @@ static WsLayout ws_layout(const rd_coalign_problem* p, int n_iter) {
         if (max_px < 8) max_px = 8;
         L.C = (p->P_pad + max_px - 1) / max_px;
         if (L.C < 1) L.C = 1;
+        const int want = pass_min_chunks(p);          // small problems: more chunks per frame to fill the SMs
+        if (want > L.C) L.C = want;
+        if (L.C > (p->P_pad + 7) / 8) L.C = (p->P_pad + 7) / 8;
         L.px_per_chunk = (((p->P_pad + L.C - 1) / L.C) + 7) & ~7;
+        L.C = (p->P_pad + L.px_per_chunk - 1) / L.px_per_chunk;      // no empty trailing chunk after the rounding
     }
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) & ~size_t(255); return o; };

@@ -50,6 +50,7 @@ constexpr int kMmaWarp = kNQ * 4, kTmaWarp = kNQ * 4 + 3;
 constexpr uint32_t kTmemCols = 512;
 constexpr uint32_t kColTile = 160, kColS = 0, kColO = 64, kColP = 128;   // per tile: S 64, O 64, P 32 columns
 constexpr float kRescaleThreshold = 8.0f;  // log2 units; p stays <= 2^8
+constexpr int kDefaultPoly = 1;            // RD_XATTN_POLY default of this kernel: 1 = all exponentials on MUFU
 
 struct XattnSmem {
     // offsets inside the 1024-byte aligned dynamic shared memory block
@@ -164,8 +165,34 @@ __device__ __forceinline__ void mask_tail64(uint32_t (&a)[32], uint32_t (&b)[32]
     }
 }
 
-// POLY: every POLY-th score pair takes the polynomial exp2 path (0 = all on MUFU)
+// 32 scores of one row -> 16 packed P words + partial row sums.  POLY: every POLY-th pair takes the polynomial path.
 template <typename T, int POLY>
+__device__ __forceinline__ void exp_half(const uint32_t (&sc)[32], uint64_t sl2_2, uint64_t nmb2, uint32_t (&pk)[16],
+                                         uint64_t (&ls2)[2]) {
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) {
+        const uint64_t x2 = ffma2(pack2(__uint_as_float(sc[i]), __uint_as_float(sc[i + 1])), sl2_2, nmb2);
+        float p0, p1;
+        if (POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == POLY - 1) {
+            ex2_poly2(x2, p0, p1);
+        } else {
+            float x0, x1;
+            unpack2(x2, x0, x1);
+            p0 = ex2(x0);
+            p1 = ex2(x1);
+        }
+        ls2[(i >> 1) & 1] = fadd2(ls2[(i >> 1) & 1], pack2(p0, p1));
+        pk[i >> 1] = PackPair<T>::pack(p0, p1);
+    }
+}
+
+// POLY: every POLY-th score pair takes the polynomial exp2 path (0 = all on MUFU).
+// SPEC: speculative exponentials.  From the second step on the exponentials are evaluated against the running row
+// maximum of the PREVIOUS steps while the row maximum of the current step is computed beside them (FMNMX on the ALU
+// pipe under the MUFU work) and PV(j-1) completes; only if the step raises some row's maximum by more than the lazy-
+// rescale threshold (2^8) -- a handful of steps per row -- is O rescaled and P recomputed.  Takes the row maximum, the
+// O_READY wait and the vote off the per-step serial path of a softmax warp (~500 of ~1400 cycles).
+template <typename T, int POLY, bool SPEC>
 __global__ void __launch_bounds__(kThreads, 1)
 xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, const XattnParams prm) {
@@ -306,6 +333,49 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             RD_TRACE(1)
             const int valid = prm.Sk - j * kBK;   // keys of this step that exist
             if (valid < kBK) mask_tail64(sa, sb, valid);
+            if (SPEC && j > 0) {
+                uint32_t pk[16];
+                uint64_t ls2[2] = {0ull, 0ull};
+                float mb = m_used * sl2;
+                uint64_t nmb2 = pack2(-mb, -mb);
+                exp_half<T, POLY>(sa, sl2_2, nmb2, pk, ls2);
+                const float m_new = fmaxf(m_used, row_max64(sa, sb));      // independent of the exponentials above
+                RD_TRACE(2)
+                mbar_wait(o_ready, (j - 1) & 1);                            // P (and O) are free once PV(j-1) has completed
+                tc_fence_after();
+                RD_TRACE(3)
+                tmem_st16(tP, pk);
+                exp_half<T, POLY>(sb, sl2_2, nmb2, pk, ls2);
+                tmem_st16(tP + 16, pk);
+                const bool need = (m_new - m_used) * sl2 > kRescaleThreshold;
+                if (__any_sync(0xffffffffu, need)) {
+                    const float f = ex2((m_used - m_new) * sl2);
+                    l *= f;
+                    tmem_st_wait();
+#pragma unroll 1
+                    for (int c = 0; c < 2; ++c) {           // rare path: keep its register footprint small
+                        uint32_t orr[32];
+                        tmem_ld32(tO + c * 32, orr);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * f);
+                        tmem_st32(tO + c * 32, orr);
+                    }
+                    m_used = m_new;
+                    mb = m_used * sl2;
+                    nmb2 = pack2(-mb, -mb);
+                    ls2[0] = ls2[1] = 0ull;
+                    exp_half<T, POLY>(sa, sl2_2, nmb2, pk, ls2);
+                    tmem_st16(tP, pk);
+                    exp_half<T, POLY>(sb, sl2_2, nmb2, pk, ls2);
+                    tmem_st16(tP + 16, pk);
+                }
+                RD_TRACE(4)
+                float a0, a1, b0, b1;
+                unpack2(ls2[0], a0, a1);
+                unpack2(ls2[1], b0, b1);
+                l += (a0 + a1) + (b0 + b1);
+            } else {
             const float m_new = fmaxf(m_used, row_max64(sa, sb));
             RD_TRACE(2)
             if (j > 0) {
@@ -336,32 +406,19 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             const float mb = m_used * sl2;
             const uint64_t nmb2 = pack2(-mb, -mb);
             uint64_t ls2[2] = {0ull, 0ull};
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            {
                 uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    const uint32_t r0 = h == 0 ? sa[i] : sb[i], r1 = h == 0 ? sa[i + 1] : sb[i + 1];
-                    const uint64_t x2 = ffma2(pack2(__uint_as_float(r0), __uint_as_float(r1)), sl2_2, nmb2);
-                    float p0, p1;
-                    if (POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == POLY - 1) {
-                        ex2_poly2(x2, p0, p1);
-                    } else {
-                        float x0, x1;
-                        unpack2(x2, x0, x1);
-                        p0 = ex2(x0);
-                        p1 = ex2(x1);
-                    }
-                    ls2[(i >> 1) & 1] = fadd2(ls2[(i >> 1) & 1], pack2(p0, p1));
-                    pk[i >> 1] = PackPair<T>::pack(p0, p1);
-                }
-                tmem_st16(tP + h * 16, pk);
+                exp_half<T, POLY>(sa, sl2_2, nmb2, pk, ls2);
+                tmem_st16(tP, pk);
+                exp_half<T, POLY>(sb, sl2_2, nmb2, pk, ls2);
+                tmem_st16(tP + 16, pk);
             }
             {
                 float a0, a1, b0, b1;
                 unpack2(ls2[0], a0, a1);
                 unpack2(ls2[1], b0, b1);
                 l += (a0 + a1) + (b0 + b1);
+            }
             }
             RD_TRACE(5)
             tmem_st_wait();
@@ -411,10 +468,10 @@ xattn_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 // ---------------------------------------------------------------------------------------------
 // host side (argument checks are done by rd_xattn_fwd in xattn_sm100.cu)
 // ---------------------------------------------------------------------------------------------
-template <typename T, int POLY>
+template <typename T, int POLY, bool SPEC>
 static int launch_k(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const XattnParams& prm, dim3 grid,
                     cudaStream_t st) {
-    auto kern = xattn_fwd_kernel<T, POLY>;
+    auto kern = xattn_fwd_kernel<T, POLY, SPEC>;
     const int smem = XattnSmem::bytes + 1024;
     static PerDeviceOnce configured;      // cudaFuncSetAttribute is per device and not a stream operation
     if (configured.needed()) {
@@ -429,11 +486,21 @@ static int launch_k(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensor
 template <typename T>
 static int launch_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const XattnParams& prm, dim3 grid,
                     int flags, cudaStream_t st) {
-    const int poly = (flags >> 8) & 0xF;       // RD_XATTN_POLY(n): 0 / 1 = off, 4 / 8 = every n-th pair
+    int poly = (flags >> 8) & 0xF;       // RD_XATTN_POLY(n): 0 = default, 1 = off, 4 / 8 = every n-th pair
+    const bool spec = ((flags >> 12) & 3) != 1;           // RD_XATTN_SPEC(n): 0 = default (on), 1 = off, 2 = on
+    if (poly == 0) poly = kDefaultPoly;
+    if (!spec) {
+        switch (poly) {
+            case 1: return launch_k<T, 0, false>(mq, mk, mv, prm, grid, st);
+            case 4: return launch_k<T, 4, false>(mq, mk, mv, prm, grid, st);
+            case 8: return launch_k<T, 8, false>(mq, mk, mv, prm, grid, st);
+            default: break;
+        }
+    }
     switch (poly) {
-        case 0: case 1: return launch_k<T, 0>(mq, mk, mv, prm, grid, st);
-        case 4: return launch_k<T, 4>(mq, mk, mv, prm, grid, st);
-        case 8: return launch_k<T, 8>(mq, mk, mv, prm, grid, st);
+        case 1: return launch_k<T, 0, true>(mq, mk, mv, prm, grid, st);
+        case 4: return launch_k<T, 4, true>(mq, mk, mv, prm, grid, st);
+        case 8: return launch_k<T, 8, true>(mq, mk, mv, prm, grid, st);
         default: set_error("RD_XATTN_POLY(%d) is not instantiated for the three-tile kernel (1, 4, 8)", poly); return RD_ERR_UNSUPPORTED;
     }
 }

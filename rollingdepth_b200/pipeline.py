@@ -305,6 +305,10 @@ class RollingDepthPipeline:
             max_vae_bs=max_vae_bs, unload_snippet=unload_snippet, verbose=verbose)
         # the decoded snippets are final: their device -> host copies overlap co-alignment (and refinement)
         out_snips = [self._to_host(snippet) for snippet in snippet_pred_ls] if is_out else None
+        fresh = is_out and self.output_mode != "pinned_views"
+        if fresh:       # worker threads pick these up as the transfers land, while the optimiser below runs
+            out_rgb = self._detach_host(out_rgb)
+            out_snips = [self._detach_host(t) for t in out_snips]
 
         # ----------------- Co-alignment (:304-318) -----------------
         # sharded runs: every rank holds every snippet after the gather in init_snippet_infer, so the aligner is the
@@ -348,12 +352,9 @@ class RollingDepthPipeline:
             self._keepalive = []
             return RollingDepthOutput(input_rgb=None, depth_pred=None, snippet_ls=None, depth_coaligned=None)
         out = RollingDepthOutput(input_rgb=out_rgb, depth_pred=out_pred, snippet_ls=out_snips, depth_coaligned=out_coal)
-        if self.output_mode != "pinned_views":
-            # host copies start as soon as the corresponding transfer has landed (per-tensor events)
-            out = RollingDepthOutput(
-                input_rgb=self._detach_host(out.input_rgb), depth_pred=self._detach_host(out.depth_pred),
-                snippet_ls=[self._detach_host(t) for t in out.snippet_ls],
-                depth_coaligned=self._detach_host(out.depth_coaligned))
+        if fresh:
+            out.depth_pred = self._detach_host(out.depth_pred)
+            out.depth_coaligned = self._detach_host(out.depth_coaligned)
         torch.cuda.current_stream(device).synchronize()
         if self._copy_stream is not None:
             self._copy_stream.synchronize()
@@ -394,25 +395,30 @@ class RollingDepthPipeline:
         return host
 
     def _detach_host(self, t: torch.Tensor) -> torch.Tensor:
-        """Fresh pageable copy of a staging view (like the reference's .cpu()), started once its transfer has
-        completed.  Large tensors are copied in row blocks by a few worker threads: under torchrun every rank runs
-        with OMP_NUM_THREADS=1, and a single-threaded first-touch copy of ~1 GB cost 270 ms per step."""
+        """Fresh pageable copy of a staging view (like the reference's .cpu()).  Nothing here blocks the calling thread:
+        worker threads wait for the tensor's transfer event and then copy it in row blocks (under torchrun every rank
+        runs with OMP_NUM_THREADS=1, and a single-threaded first-touch copy of ~1 GB cost 270 ms per step), so the host
+        copies of the snippets run while the optimiser's launches are still being issued; forward() joins them at the end."""
         ev = self._stage_events.pop(t.data_ptr(), None)
         if ev is None:
             return t
-        ev.synchronize()
         out = torch.empty(t.shape, dtype=t.dtype, device="cpu")
         nbytes = t.numel() * t.element_size()
         rows = t.shape[0] if t.dim() > 0 else 1
-        if nbytes < (16 << 20) or rows < 2:
-            out.copy_(t)
-            return out
         n_out = self.shard.world if self.output_ranks is None else max(1, len(self.output_ranks))
         pool = _host_copy_pool(n_out)
+
+        def copy_block(dst, src):
+            ev.synchronize()
+            dst.copy_(src)
+
+        if nbytes < (16 << 20) or rows < 2:
+            self._host_copies.append(pool.submit(copy_block, out, t))
+            return out
         n_blk = min(rows, 4 * pool._max_workers)
         step = (rows + n_blk - 1) // n_blk
         for r0 in range(0, rows, step):
-            self._host_copies.append(pool.submit(out[r0:r0 + step].copy_, t[r0:r0 + step]))
+            self._host_copies.append(pool.submit(copy_block, out[r0:r0 + step], t[r0:r0 + step]))
         return out
 
     # ------------------------------------------------------------------ initial snippet inference (:356-463)

@@ -75,7 +75,8 @@ XATTN_SHAPES = [
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("shape", XATTN_SHAPES)
-@pytest.mark.parametrize("flags", [0, 2, 4 << 8, 2 << 4, 3 << 4, (3 << 4) | (4 << 8)])
+@pytest.mark.parametrize("flags", [0, 2, 4 << 8, 2 << 4, 3 << 4, (3 << 4) | (4 << 8), (3 << 4) | (1 << 12),
+                                   (3 << 4) | (1 << 12) | (8 << 8), (3 << 4) | (2 << 12) | (8 << 8)])
 def test_xattn_tcgen05_matches_oracle(shape, dtype, flags):
     from rollingdepth_b200 import ops
     dev = _dev()
@@ -166,8 +167,10 @@ def test_xattn_head_major_strides_and_scale():
     assert float((out.float() - ref).abs().max()) <= 2e-2
 
 
-def test_xattn_large_logits_trigger_rescale():
-    """Scores that keep growing along the key axis force the lazy O-rescale path on every tile."""
+@pytest.mark.parametrize("flags", [0, 3 << 4, (3 << 4) | (1 << 12), (3 << 4) | (4 << 8)])
+def test_xattn_large_logits_trigger_rescale(flags):
+    """Scores that keep growing along the key axis force the lazy O-rescale path on every tile (in the three-tile kernel
+    with speculative exponentials: the recompute-P path)."""
     from rollingdepth_b200 import ops
     dev = _dev()
     B, S, H, D = 1, 1024, 2, 64
@@ -176,7 +179,7 @@ def test_xattn_large_logits_trigger_rescale():
     k = torch.randn(B, S, H, D, generator=g) * torch.linspace(0.5, 6.0, S)[None, :, None, None]
     v = torch.randn(B, S, H, D, generator=g)
     q, k, v = [t.half().to(dev) for t in (q, k, v)]
-    out = ops.xattn_fwd(q, k, v)
+    out = ops.xattn_fwd(q, k, v, flags=flags)
     ref = _oracle_attn(q, k, v)
     assert float((out.float() - ref).abs().max()) <= 2e-2
 
