@@ -65,10 +65,6 @@ int rd_device_arch(void);
 /* query tiles per CTA: 0 = chosen by grid size (three 128-row tiles on many-wave grids of long sequences, else two),
  * 2 / 3 = force (A/B measurements; the parity tests run both) */
 #define RD_XATTN_TILES(n) (((n) & 3) << 4)
-/* speculative exponentials in the three-tile kernel (exp against the previous steps' row maximum while the current
- * step's maximum is computed beside it; P recomputed on the rare step that raises a maximum by more than 2^8):
- * 0 = default (on), 1 = off, 2 = on (A/B measurements; the parity tests run both) */
-#define RD_XATTN_SPEC(n) (((n) & 3) << 12)
 int rd_xattn_fwd(const void* q, const void* k, const void* v, void* o,
                  int B, int H, int Sq, int Sk, int D,
                  int64_t q_sb, int64_t q_ss, int64_t q_sh,

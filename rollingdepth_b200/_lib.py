@@ -25,10 +25,6 @@ def XATTN_TILES(n: int) -> int:
 def XATTN_POLY(n: int) -> int:
     return (n & 0xF) << 8
 
-
-def XATTN_SPEC(n: int) -> int:
-    return (n & 3) << 12
-
 _DTYPES = {torch.float32: RD_F32, torch.float16: RD_F16, torch.bfloat16: RD_BF16}
 
 

@@ -75,8 +75,7 @@ XATTN_SHAPES = [
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("shape", XATTN_SHAPES)
-@pytest.mark.parametrize("flags", [0, 2, 4 << 8, 2 << 4, 3 << 4, (3 << 4) | (4 << 8), (3 << 4) | (1 << 12),
-                                   (3 << 4) | (1 << 12) | (8 << 8), (3 << 4) | (2 << 12) | (8 << 8)])
+@pytest.mark.parametrize("flags", [0, 2, 4 << 8, 2 << 4, 3 << 4, (3 << 4) | (4 << 8), (3 << 4) | (8 << 8)])
 def test_xattn_tcgen05_matches_oracle(shape, dtype, flags):
     from rollingdepth_b200 import ops
     dev = _dev()
@@ -167,10 +166,9 @@ def test_xattn_head_major_strides_and_scale():
     assert float((out.float() - ref).abs().max()) <= 2e-2
 
 
-@pytest.mark.parametrize("flags", [0, 3 << 4, (3 << 4) | (1 << 12), (3 << 4) | (4 << 8)])
+@pytest.mark.parametrize("flags", [0, 3 << 4, (3 << 4) | (4 << 8)])
 def test_xattn_large_logits_trigger_rescale(flags):
-    """Scores that keep growing along the key axis force the lazy O-rescale path on every tile (in the three-tile kernel
-    with speculative exponentials: the recompute-P path)."""
+    """Scores that keep growing along the key axis force the lazy O-rescale path on every tile (both kernels)."""
     from rollingdepth_b200 import ops
     dev = _dev()
     B, S, H, D = 1, 1024, 2, 64
