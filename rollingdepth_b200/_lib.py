@@ -80,6 +80,7 @@ SIGNATURES = {
     "rd_reduce_scratch_bytes": (_I64, []),
     "rd_global_min": (_I, [_PP, _PRB, _P, _P, _P]),
     "rd_coalign_prep": (_I, [_PP, _PRB, _P, _P, _P]),
+    "rd_coalign_set_config": (_I, [_I]),
     "rd_coalign_workspace_bytes": (_I64, [_PRB, _I]),
     "rd_coalign_optimize": (_I, [_P, _PRB, _HP, _P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I64, _P]),
     "rd_coalign_begin": (_I, [_PRB, _P, _P, _P, _P, _P, _P, _I, _I, _P, _I64, _P]),

@@ -591,6 +591,320 @@ __global__ void __launch_bounds__(kPassThreads, kCtasPerSm) coalign_pass_kernel(
     }
 }
 
+// =============================================================================================
+// The fused optimisation pass, contribution-packed organisation (cfg 2 / 3)
+// =============================================================================================
+// One thread = ONE pixel; the two lanes of every packed fp32x2 value are two CONTRIBUTIONS (i, i + RH) of that pixel
+// instead of two pixels of one contribution.  Same packed instruction count per (contribution, pixel), but a thread
+// carries accumulators for half as many (contribution, lane) pairs: 4 * RH packed registers instead of 4 * R, which
+// removes the spills of the pixel-packed kernel (168 registers, 0.9 M local loads per launch at R = 9) and lets 16
+// warps per SM stay resident instead of 12.  Contributions that do not exist for a frame (clip ends) and the odd
+// dummy contribution are arithmetic no-ops -- x = 0 from a zero-filled staged row, s = t = 0, a 0 / 1 mask folded into
+// the sign constants -- so interior and boundary frames run the same branch-free code.
+// The cross-chunk hand-over is a single-thread release / acquire (bar.sync -> fence + ticket by one thread -> bar.sync)
+// instead of fences executed by every thread.
+template <int RH>
+struct PassAccC {
+    uint64_t A0[RH], A1[RH], D0[RH], D1[RH];   // lane 0: contribution i, lane 1: contribution i + RH
+    uint64_t l1;
+    float l2, fa, fb, tmin, tmax;
+};
+
+template <typename T>
+__device__ __forceinline__ uint64_t lds_two_rows(const T* lo, const T* hi) {
+    return pk2(Cvt<T>::to_f(*lo), Cvt<T>::to_f(*hi));
+}
+
+template <typename T, int RH, int kPassThreads, int kCtasPerSm>
+__global__ void __launch_bounds__(kPassThreads, kCtasPerSm) coalign_pass_cp_kernel(const PassParams p) {
+    constexpr int RM = 2 * RH;
+    constexpr int NV = 4 * RM + kFrameStats;
+    constexpr int NROUND = (4 * RM + 4 + 31) / 32;       // summed values: 4 per contribution + fa, fb, l1, l2
+    extern __shared__ __align__(128) unsigned char pass_smem[];
+    __shared__ __align__(8) uint64_t sh_bar;
+    __shared__ int sh_row[RM];
+    __shared__ float sh_s[RM], sh_t[RM], sh_soft[RM];
+    __shared__ float sh_red[kPassThreads / 32][NROUND * 32 + 2];
+    __shared__ float sh_tot[NV];
+    __shared__ int sh_last;
+
+    const int tid = threadIdx.x;
+    const int ch = blockIdx.x;
+    const int f = p.f_begin + blockIdx.y;
+    const int R = p.R, nt = p.n_total;
+    const int pitch = p.px_per_chunk;
+    const int px0 = ch * pitch;
+    const int npx = min(p.P_pad, px0 + pitch) - px0;              // staged pixels (multiple of 8)
+    const int nvalid = min(p.P, px0 + npx) - px0;                 // of which real pixels
+    T* stage = reinterpret_cast<T*>(pass_smem);                   // [RM][pitch]
+
+    // ---------------- kick off the bulk copies of this (frame, chunk)
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pass_smem_u32(&sh_bar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        uint32_t total = 0;
+        for (int c = 0; c < R; ++c) {
+            const int g = c / p.w, j = c - g * p.w;
+            const int k = f - j * p.d[g];
+            if (k >= 0 && k < p.n[g]) total += (uint32_t)(npx * sizeof(T));
+        }
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pass_smem_u32(&sh_bar)), "r"(total) : "memory");
+        for (int c = 0; c < R; ++c) {
+            const int g = c / p.w, j = c - g * p.w;
+            const int k = f - j * p.d[g];
+            if (k >= 0 && k < p.n[g]) {
+                const T* src = reinterpret_cast<const T*>(p.x) + ((size_t)(p.row0[g] + k) * p.w + j) * p.P_pad + px0;
+                bulk_g2s(stage + (size_t)c * pitch, src, (uint32_t)(npx * sizeof(T)), &sh_bar);
+            }
+        }
+    }
+
+    // ---------------- prologue: parameters of the <= R snippets touching this frame (overlaps the copies)
+    if (tid >= 32 && tid < 32 + RM) {
+        const int c = tid - 32;
+        int row = -1;
+        float s = 0.f, t = 0.f, soft = 0.f;
+        if (c < R) {
+            const int g = c / p.w, j = c - g * p.w;
+            const int d = p.d[g];
+            const int k = f - j * d;
+            if (k >= 0 && k < p.n[g]) {
+                row = p.row0[g] + k;
+                s = __ldcg(p.theta_in + row);
+                t = __ldcg(p.theta_in + nt + row);
+                const float ng = (float)p.n[g];
+                if (p.apply_update) {
+                    float ms = __ldcg(p.theta_in + 2 * nt + row), mt = __ldcg(p.theta_in + 3 * nt + row);
+                    float vs = __ldcg(p.theta_in + 4 * nt + row), vt = __ldcg(p.theta_in + 5 * nt + row);
+                    float gs = 0.f, gt = 0.f;
+                    for (int jj = 0; jj < p.w; ++jj) {
+                        const int fp = k + jj * d;
+                        const float2 gg = __ldcg(reinterpret_cast<const float2*>(p.gterm_in) + (size_t)fp * R + g * p.w + jj);
+                        gs += gg.x;
+                        gt += gg.y;
+                    }
+                    gs += -2.f * p.lmda2 * fmaxf(1.f - s, 0.f) / ng;
+                    gt += 2.f * p.lmda3 * t / ng;
+                    adam_update(s, ms, vs, gs, p);
+                    adam_update(t, mt, vt, gt, p);
+                    if (ch == 0) {
+                        // every frame touching this snippet writes the same bits (deterministic recompute)
+                        p.theta_out[row] = s;           p.theta_out[nt + row] = t;
+                        p.theta_out[2 * nt + row] = ms; p.theta_out[3 * nt + row] = mt;
+                        p.theta_out[4 * nt + row] = vs; p.theta_out[5 * nt + row] = vt;
+                    }
+                }
+                if (j == 0) {
+                    const float hinge = fmaxf(1.f - s, 0.f);
+                    soft = (p.lmda2 * hinge * hinge + p.lmda3 * t * t) / ng;
+                }
+            }
+        }
+        sh_row[c] = row;
+        sh_s[c] = row >= 0 ? s : 0.f;       // absent contribution: y = 0 * 0 + 0 (below the clip => no gradient either)
+        sh_t[c] = row >= 0 ? t : 0.f;
+        sh_soft[c] = soft;
+    }
+    __syncthreads();
+    if (ch == 0 && tid == 0) {
+        float soft = 0.f;
+        for (int c = 0; c < R; ++c) soft += sh_soft[c];
+        p.hist_frame[(size_t)f * 4 + 1] = soft;
+    }
+
+    uint64_t sc2[RH], tc2[RH], vm2[RH];
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < RH; ++i) {
+        const bool v0 = sh_row[i] >= 0, v1 = sh_row[i + RH] >= 0;
+        sc2[i] = pk2(sh_s[i], sh_s[i + RH]);
+        tc2[i] = pk2(sh_t[i], sh_t[i + RH]);
+        vm2[i] = pk2(v0 ? 1.f : 0.f, v1 ? 1.f : 0.f);
+        cnt += (int)v0 + (int)v1;
+    }
+    const float cntf = (float)cnt;
+    const float rcnt = __fdiv_rn(1.f, cntf);
+    const bool single = cnt <= 1;       // y == target exactly: the data term has zero gradient (sign(0) = 0)
+    if (cnt != RM) {                    // CTA-uniform: zero-fill the staged rows of absent contributions (x = 0)
+        for (int c = 0; c < RM; ++c) {
+            if (sh_row[c] >= 0) continue;
+            uint4* z = reinterpret_cast<uint4*>(stage + (size_t)c * pitch);
+            for (int q = tid; q < (int)(npx * sizeof(T) / 16); q += kPassThreads) z[q] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+    }
+
+    // ---------------- wait for the staged rows
+    {
+        uint32_t ok = 0;
+        int spins = 0;
+        do {
+            asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0, 100000;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                         : "=r"(ok) : "r"(pass_smem_u32(&sh_bar)) : "memory");
+            if (!ok && ++spins > 4000000) __trap();
+        } while (!ok);
+    }
+
+    // ---------------- main loop: one pixel per thread per step, all contributions, from shared memory
+    PassAccC<RH> acc;
+#pragma unroll
+    for (int i = 0; i < RH; ++i) { acc.A0[i] = acc.A1[i] = acc.D0[i] = acc.D1[i] = 0ull; }
+    acc.l1 = 0ull;
+    acc.l2 = acc.fa = acc.fb = 0.f;
+    acc.tmin = INFINITY;
+    acc.tmax = -INFINITY;
+    const T* hi_rows = stage + (size_t)RH * pitch;
+    for (int q = tid; q < nvalid; q += kPassThreads) {
+        uint64_t xv[RH], iv[RH];
+        uint64_t sy2 = 0ull, si2 = 0ull;
+#pragma unroll
+        for (int i = 0; i < RH; ++i) {
+            xv[i] = lds_two_rows<T>(stage + (size_t)i * pitch + q, hi_rows + (size_t)i * pitch + q);
+            const uint64_t y = ffma2(sc2[i], xv[i], tc2[i]);
+            float y0, y1;
+            upk2(y, y0, y1);
+            iv[i] = pk2(rcp_fast(fmaxf(y0, 1e-3f)), rcp_fast(fmaxf(y1, 1e-3f)));
+            sy2 = ffma2(y, vm2[i], sy2);
+            si2 = ffma2(iv[i], vm2[i], si2);
+        }
+        float sya, syb, sia, sib;
+        upk2(sy2, sya, syb);
+        upk2(si2, sia, sib);
+        const float sy = sya + syb, si = sia + sib;
+        // target = sum / cnt: reciprocal product + one Newton step (correctly rounded quotient)
+        float tg = sy * rcnt, td = si * rcnt;
+        tg = fmaf(fmaf(-cntf, tg, sy), rcnt, tg);
+        td = fmaf(fmaf(-cntf, td, si), rcnt, td);
+        acc.fa += fabsf(tg);
+        acc.fb += fabsf(td);
+        acc.tmin = fminf(acc.tmin, tg);
+        acc.tmax = fmaxf(acc.tmax, tg);
+        if (single) continue;           // CTA-uniform
+        const uint64_t tg2 = bc2(tg), td2 = bc2(td);
+#pragma unroll
+        for (int i = 0; i < RH; ++i) {
+            const uint64_t x = xv[i];
+            const uint64_t y = ffma2(sc2[i], x, tc2[i]);
+            const uint64_t r1 = fsub2(y, tg2);
+            float v0, v1;
+            upk2(vm2[i], v0, v1);
+            const uint64_t sg = signed_mag2(v0, v1, r1);                          // sign(y - target), 0 where absent
+            acc.l1 = ffma2(sg, r1, acc.l1);                                        // |r1|
+            acc.A0[i] = fadd2(acc.A0[i], sg);
+            acc.A1[i] = ffma2(sg, x, acc.A1[i]);
+            const uint64_t in = iv[i];
+            const uint64_t r2 = fsub2(in, td2);
+            float y0, y1, q0f, q1f;
+            upk2(y, y0, y1);
+            upk2(r2, q0f, q1f);
+            acc.l2 = fmaf(fabsf(q0f), v0, acc.l2);
+            acc.l2 = fmaf(fabsf(q1f), v1, acc.l2);
+            // d(1/clamp(y, 1e-3))/dy = -1/y^2 where y >= 1e-3, else 0; absent contributions have y = 0 < 1e-3
+            const uint64_t sm = signed_mag2(y0 >= 1e-3f ? 1.0f : 0.0f, y1 >= 1e-3f ? 1.0f : 0.0f, r2);
+            const uint64_t w = fmul2(in, in);
+            acc.D0[i] = ffma2(sm, w, acc.D0[i]);
+            acc.D1[i] = ffma2(sm, fmul2(w, x), acc.D1[i]);
+        }
+    }
+
+    // ---------------- block reduction: butterfly within warps, fixed-order sum across warps
+    const int lane = tid & 31, warp = tid >> 5;
+    {
+        float slot[NROUND][32];
+#pragma unroll
+        for (int r = 0; r < NROUND; ++r)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) slot[r][i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < RH; ++i) {
+            float lo, hi;
+            const int c0 = i, c1 = i + RH;
+            upk2(acc.A0[i], lo, hi); slot[(4 * c0 + 0) / 32][(4 * c0 + 0) % 32] = lo; slot[(4 * c1 + 0) / 32][(4 * c1 + 0) % 32] = hi;
+            upk2(acc.A1[i], lo, hi); slot[(4 * c0 + 1) / 32][(4 * c0 + 1) % 32] = lo; slot[(4 * c1 + 1) / 32][(4 * c1 + 1) % 32] = hi;
+            upk2(acc.D0[i], lo, hi); slot[(4 * c0 + 2) / 32][(4 * c0 + 2) % 32] = lo; slot[(4 * c1 + 2) / 32][(4 * c1 + 2) % 32] = hi;
+            upk2(acc.D1[i], lo, hi); slot[(4 * c0 + 3) / 32][(4 * c0 + 3) % 32] = lo; slot[(4 * c1 + 3) / 32][(4 * c1 + 3) % 32] = hi;
+        }
+        float l1a, l1b;
+        upk2(acc.l1, l1a, l1b);
+        slot[(4 * RM + 0) / 32][(4 * RM + 0) % 32] = acc.fa;
+        slot[(4 * RM + 1) / 32][(4 * RM + 1) % 32] = acc.fb;
+        slot[(4 * RM + 2) / 32][(4 * RM + 2) % 32] = l1a + l1b;
+        slot[(4 * RM + 3) / 32][(4 * RM + 3) % 32] = acc.l2;
+#pragma unroll
+        for (int r = 0; r < NROUND; ++r) {
+            const float tot = warp_transpose_sum<32>(slot[r], lane);
+            sh_red[warp][r * 32 + lane] = tot;
+        }
+        const float mn = warp_min(acc.tmin), mx = warp_max(acc.tmax);
+        if (lane == 0) { sh_red[warp][NROUND * 32] = mn; sh_red[warp][NROUND * 32 + 1] = mx; }
+    }
+    __syncthreads();
+    float* part_f = p.part + (size_t)f * p.C * NV;
+    if (tid < NV) {
+        // NV layout: [4*c + {A0,A1,D0,D1}] for c < RM, then fa, fb, l1, l2, tmin, tmax, pad, pad
+        const int q = tid - 4 * RM;
+        float v;
+        if (q == 4 || q == 5) {
+            v = sh_red[0][NROUND * 32 + (q - 4)];
+            for (int w = 1; w < kPassThreads / 32; ++w) {
+                const float o = sh_red[w][NROUND * 32 + (q - 4)];
+                v = (q == 4) ? fminf(v, o) : fmaxf(v, o);
+            }
+        } else if (q >= 6) {
+            v = 0.f;
+        } else {
+            v = 0.f;
+#pragma unroll
+            for (int w = 0; w < kPassThreads / 32; ++w) v += sh_red[w][tid];
+        }
+        if (p.C == 1) sh_tot[tid] = v;
+        else part_f[(size_t)ch * NV + tid] = v;
+    }
+    if (p.C > 1) {
+        __syncthreads();                 // the partials of this CTA are written (CTA scope) ...
+        if (tid == 0) {
+            __threadfence();             // ... one thread publishes them at GPU scope (cumulative release) and takes a ticket
+            const unsigned prev = atomicAdd(&p.counter[f], 1u);
+            __threadfence();             // acquire side for the last chunk: the other chunks' partials are visible below
+            sh_last = (prev == (unsigned)(p.C - 1));
+        }
+        __syncthreads();
+        if (!sh_last) return;
+        if (tid < NV) {
+            float v = __ldcg(part_f + tid);
+            const int q = tid - 4 * RM;
+            for (int c2 = 1; c2 < p.C; ++c2) {
+                const float o = __ldcg(part_f + (size_t)c2 * NV + tid);
+                v = (q == 4) ? fminf(v, o) : (q == 5) ? fmaxf(v, o) : v + o;
+            }
+            sh_tot[tid] = v;
+        }
+        if (tid == 0) p.counter[f] = 0;
+    }
+    __syncthreads();
+
+    // ---------------- last chunk of the frame: per-frame scales, gradient terms, loss term ----
+    const float a = sh_tot[4 * RM + 0] * p.inv_P;   // mean_p |target|   (depth_aligner.py:197)
+    const float b = sh_tot[4 * RM + 1] * p.inv_P;   // mean_p |target_depth|
+    const float ia = __fdiv_rn(1.f, a), ib = __fdiv_rn(1.f, b);
+    if (tid < R) {
+        float2 gg = make_float2(0.f, 0.f);
+        if (sh_row[tid] >= 0) {
+            const float a0 = sh_tot[4 * tid + 0], a1 = sh_tot[4 * tid + 1];
+            const float d0 = sh_tot[4 * tid + 2], d1 = sh_tot[4 * tid + 3];
+            gg.x = p.ls_over_Z * (a1 * ia - p.dlw * d1 * ib);   // d loss / d s  (data term)
+            gg.y = p.ls_over_Z * (a0 * ia - p.dlw * d0 * ib);   // d loss / d t
+        }
+        reinterpret_cast<float2*>(p.gterm_out)[(size_t)f * R + tid] = gg;
+    }
+    if (tid == 0) {
+        float* h = p.hist_frame + (size_t)f * 4;
+        h[0] = p.ls_over_Z * (sh_tot[4 * RM + 2] * ia + p.dlw * sh_tot[4 * RM + 3] * ib);
+        h[2] = sh_tot[4 * RM + 4];
+        h[3] = sh_tot[4 * RM + 5];
+    }
+}
+
 // final Adam update for snippets whose first frame lies in [f_begin, f_end)
 __global__ void coalign_final_update_kernel(PassParams p, int f_begin, int f_end, float* s, float* t, float* m_s,
                                             float* m_t, float* v_s, float* v_t) {
@@ -811,18 +1125,35 @@ static int pick_rm(int R) {
 
 // working set of one iteration above which the subsampled snippets no longer stay in the 126 MB L2
 constexpr long long kPassL2Bytes = 100ll << 20;
+static int g_pass_cfg_forced = -2;       // -2: not read yet, -1: automatic, 0..4: forced (RD_COALIGN_CFG / rd_coalign_set_config)
 static int pass_cfg(const rd_coalign_problem* p) {
-    static int forced = -2;
-    if (forced == -2) {
+    if (g_pass_cfg_forced == -2) {
         const char* e = getenv("RD_COALIGN_CFG");
-        forced = e ? atoi(e) : -1;
-        if (forced < -1 || forced > 1) forced = -1;
+        g_pass_cfg_forced = e ? atoi(e) : -1;
+        if (g_pass_cfg_forced < -1 || g_pass_cfg_forced > 4) g_pass_cfg_forced = -1;
     }
-    if (forced >= 0) return forced;
+    if (g_pass_cfg_forced >= 0) return g_pass_cfg_forced;
     const long long bytes = (long long)p->n_total * p->w * p->P_pad * (p->dtype == RD_F32 ? 4 : 2);
     return bytes > kPassL2Bytes ? 1 : 0;
 }
-static int pass_smem_budget(const rd_coalign_problem* p) { return pass_cfg(p) == 1 ? 65536 : 98304; }
+// cfg 0 / 1: pixel-packed kernel (192 x 2 / 128 x 3 CTAs per SM); cfg 2 / 3: contribution-packed kernel (128 x 4 / 256 x 2);
+// cfg 4: contribution-packed, one 512-thread CTA per SM (short clips: about one frame per SM, the launch is latency-bound
+// and the only parallelism left is inside the frame)
+static int pass_smem_budget(const rd_coalign_problem* p) {
+    switch (pass_cfg(p)) {
+        case 1: return 65536;
+        case 2: return 55 * 1024;
+        case 3: return 110 * 1024;
+        case 4: return 200 * 1024;
+        default: return 98304;
+    }
+}
+static int pick_rh(int R) {          // contribution pairs of the contribution-packed kernel
+    const int opts[] = {2, 3, 4, 5, 6, 8};
+    for (int o : opts)
+        if ((R + 1) / 2 <= o) return o;
+    return -1;
+}
 
 // Chunks per frame beyond what shared memory requires.  With one CTA per frame a 150-frame clip is 150 CTAs of 6 warps
 // on 148 SMs: every SM runs latency-bound at 1.5 warps per scheduler, and two SMs run two frames.  Splitting frames
@@ -840,12 +1171,14 @@ static int pass_min_chunks(const rd_coalign_problem* p) {
 static WsLayout ws_layout(const rd_coalign_problem* p, int n_iter) {
     WsLayout L{};
     const int R = p->G * p->w;
-    L.RM = pick_rm(R);
     L.cfg = pass_cfg(p);
+    L.RM = L.cfg >= 2 ? (pick_rh(R) < 0 ? -1 : 2 * pick_rh(R)) : pick_rm(R);
     L.NV = 4 * (L.RM < 0 ? 16 : L.RM) + kFrameStats;
-    {   // pixels per (frame, chunk): all R rows of a chunk are staged in shared memory at once
+    {   // pixels per (frame, chunk): all rows of a chunk are staged in shared memory at once (cfg 2 / 3 also stage the
+        // zero rows of the dummy / absent contributions)
         const int es = p->dtype == RD_F32 ? 4 : 2;
-        int max_px = pass_smem_budget(p) / (R * es);
+        const int rows = L.cfg >= 2 && L.RM > 0 ? L.RM : R;
+        int max_px = pass_smem_budget(p) / (rows * es);
         max_px &= ~7;
         if (max_px < 8) max_px = 8;
         L.C = (p->P_pad + max_px - 1) / max_px;
@@ -890,8 +1223,39 @@ static int launch_pass_k(const PassParams& pp, int cfg, dim3 grid, cudaStream_t 
     return launch_pass_c<T, RM, 192, 2>(pp, grid, st);
 }
 
+template <typename T, int RH, int NT, int NCTA>
+static int launch_pass_cp(const PassParams& pp, dim3 grid, cudaStream_t st) {
+    auto kern = coalign_pass_cp_kernel<T, RH, NT, NCTA>;
+    const int smem = 2 * RH * pp.px_per_chunk * (int)sizeof(T);
+    static PerDeviceOnce configured;      // cudaFuncSetAttribute is per device and not a stream operation
+    if (configured.needed()) {
+        RD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, NCTA == 1 ? 204 * 1024 : 112 * 1024));
+        configured.done();
+    }
+    kern<<<grid, NT, smem, st>>>(pp);
+    RD_LAUNCH_CHECK("coalign_pass_cp_kernel");
+    return RD_OK;
+}
+template <typename T, int RH>
+static int launch_pass_cpk(const PassParams& pp, int cfg, dim3 grid, cudaStream_t st) {
+    if (cfg == 4) return launch_pass_cp<T, RH, 512, 1>(pp, grid, st);
+    if (cfg == 3) return launch_pass_cp<T, RH, 256, 2>(pp, grid, st);
+    return launch_pass_cp<T, RH, 128, 4>(pp, grid, st);
+}
+
 template <typename T>
 static int launch_pass_t(const PassParams& pp, int RM, int cfg, dim3 grid, cudaStream_t st) {
+    if (cfg >= 2) {
+        switch (RM / 2) {
+            case 2: return launch_pass_cpk<T, 2>(pp, cfg, grid, st);
+            case 3: return launch_pass_cpk<T, 3>(pp, cfg, grid, st);
+            case 4: return launch_pass_cpk<T, 4>(pp, cfg, grid, st);
+            case 5: return launch_pass_cpk<T, 5>(pp, cfg, grid, st);
+            case 6: return launch_pass_cpk<T, 6>(pp, cfg, grid, st);
+            case 8: return launch_pass_cpk<T, 8>(pp, cfg, grid, st);
+            default: set_error("unsupported G*w"); return RD_ERR_UNSUPPORTED;
+        }
+    }
     switch (RM) {
         case 4:  return launch_pass_k<T, 4>(pp, cfg, grid, st);
         case 6:  return launch_pass_k<T, 6>(pp, cfg, grid, st);
@@ -1019,6 +1383,15 @@ int rd_coalign_prep(const void* const* host_snip_ptrs, const rd_coalign_problem*
     }
     RD_LAUNCH_CHECK("prep_kernel");
     return RD_OK;
+}
+
+int rd_coalign_set_config(int cfg) {
+    RD_CHECK_ARG(cfg >= -1 && cfg <= 4, "cfg must be -1 (automatic) or 0..4");
+    (void)pass_cfg;                       // make sure the environment default has been read first
+    if (g_pass_cfg_forced == -2) { rd_coalign_problem dummy{}; dummy.n_total = 1; dummy.w = 1; dummy.P_pad = 8; (void)pass_cfg(&dummy); }
+    const int prev = g_pass_cfg_forced;
+    g_pass_cfg_forced = cfg;
+    return prev + 2;                      // >= 1 on success (previous setting + 2), so that negative values stay errors
 }
 
 int64_t rd_coalign_workspace_bytes(const rd_coalign_problem* p, int n_iter) {

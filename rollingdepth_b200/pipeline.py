@@ -309,6 +309,8 @@ class RollingDepthPipeline:
         if fresh:       # worker threads pick these up as the transfers land, while the optimiser below runs
             out_rgb = self._detach_host(out_rgb)
             out_snips = [self._detach_host(t) for t in out_snips]
+            late_shape = (seq_len, 1, *snippet_pred_ls[0].shape[-2:])
+            pre_late = [self._prefault(late_shape, self.dtype) for _ in range(2)]   # depth_coaligned, depth_pred
 
         # ----------------- Co-alignment (:304-318) -----------------
         # sharded runs: every rank holds every snippet after the gather in init_snippet_infer, so the aligner is the
@@ -353,8 +355,8 @@ class RollingDepthPipeline:
             return RollingDepthOutput(input_rgb=None, depth_pred=None, snippet_ls=None, depth_coaligned=None)
         out = RollingDepthOutput(input_rgb=out_rgb, depth_pred=out_pred, snippet_ls=out_snips, depth_coaligned=out_coal)
         if fresh:
-            out.depth_pred = self._detach_host(out.depth_pred)
-            out.depth_coaligned = self._detach_host(out.depth_coaligned)
+            out.depth_coaligned = self._detach_host(out.depth_coaligned, pre_late[0])
+            out.depth_pred = self._detach_host(out.depth_pred, pre_late[1])
         torch.cuda.current_stream(device).synchronize()
         if self._copy_stream is not None:
             self._copy_stream.synchronize()
@@ -394,31 +396,57 @@ class RollingDepthPipeline:
         self._stage_events[host.data_ptr()] = ev
         return host
 
-    def _detach_host(self, t: torch.Tensor) -> torch.Tensor:
+    def _host_pool(self):
+        n_out = self.shard.world if self.output_ranks is None else max(1, len(self.output_ranks))
+        return _host_copy_pool(n_out)
+
+    @staticmethod
+    def _row_blocks(t: torch.Tensor, n_workers: int):
+        nbytes = t.numel() * t.element_size()
+        rows = t.shape[0] if t.dim() > 0 else 1
+        if nbytes < (16 << 20) or rows < 2:
+            return [(0, rows)]
+        n_blk = min(rows, 4 * n_workers)
+        step = (rows + n_blk - 1) // n_blk
+        return [(r0, min(r0 + step, rows)) for r0 in range(0, rows, step)]
+
+    def _prefault(self, shape, dtype):
+        """A fresh pageable host tensor whose pages are touched by the worker threads NOW (while the GPU is still busy
+        with the optimiser), so that the copy of a late result into it is a plain memcpy instead of ~25 k page faults
+        on the critical path at the end of the step.  Returns (tensor, {row block: future})."""
+        pool = self._host_pool()
+        out = torch.empty(tuple(shape), dtype=dtype, device="cpu")
+        futs = {}
+        for r0, r1 in self._row_blocks(out, pool._max_workers):
+            futs[(r0, r1)] = pool.submit(out[r0:r1].zero_) if out.dim() > 0 else pool.submit(out.zero_)
+        self._host_copies.extend(futs.values())
+        return out, futs
+
+    def _detach_host(self, t: torch.Tensor, pre=None) -> torch.Tensor:
         """Fresh pageable copy of a staging view (like the reference's .cpu()).  Nothing here blocks the calling thread:
         worker threads wait for the tensor's transfer event and then copy it in row blocks (under torchrun every rank
         runs with OMP_NUM_THREADS=1, and a single-threaded first-touch copy of ~1 GB cost 270 ms per step), so the host
-        copies of the snippets run while the optimiser's launches are still being issued; forward() joins them at the end."""
+        copies of the snippets run while the optimiser's launches are still being issued; forward() joins them at the end.
+        `pre`: a (tensor, futures) pair from `_prefault` to copy into."""
         ev = self._stage_events.pop(t.data_ptr(), None)
         if ev is None:
             return t
-        out = torch.empty(t.shape, dtype=t.dtype, device="cpu")
-        nbytes = t.numel() * t.element_size()
-        rows = t.shape[0] if t.dim() > 0 else 1
-        n_out = self.shard.world if self.output_ranks is None else max(1, len(self.output_ranks))
-        pool = _host_copy_pool(n_out)
+        pool = self._host_pool()
+        if pre is not None and tuple(pre[0].shape) == tuple(t.shape) and pre[0].dtype == t.dtype:
+            out, touched = pre
+        else:
+            out, touched = torch.empty(t.shape, dtype=t.dtype, device="cpu"), {}
 
-        def copy_block(dst, src):
+        def copy_block(dst, src, after):
+            if after is not None:
+                after.result()          # the block's pages have been touched (submitted earlier: cannot deadlock)
             ev.synchronize()
             dst.copy_(src)
 
-        if nbytes < (16 << 20) or rows < 2:
-            self._host_copies.append(pool.submit(copy_block, out, t))
-            return out
-        n_blk = min(rows, 4 * pool._max_workers)
-        step = (rows + n_blk - 1) // n_blk
-        for r0 in range(0, rows, step):
-            self._host_copies.append(pool.submit(copy_block, out[r0:r0 + step], t[r0:r0 + step]))
+        blocks = list(touched) if touched else self._row_blocks(out, pool._max_workers)
+        for r0, r1 in blocks:
+            dst, src = (out[r0:r1], t[r0:r1]) if out.dim() > 0 else (out, t)
+            self._host_copies.append(pool.submit(copy_block, dst, src, touched.get((r0, r1))))
         return out
 
     # ------------------------------------------------------------------ initial snippet inference (:356-463)

@@ -24,6 +24,10 @@ def resize_frames(img: torch.Tensor, size: List[int], resample_method: str = "BI
     mode = _interp_mode(resample_method)
     if mode.startswith("nearest"):
         return F.interpolate(img, size=tuple(size), mode=mode)
+    if img.device.type == "cpu" and img.dtype in (torch.float16, torch.bfloat16):
+        # torch has no 16-bit antialiased resampling kernel on CPU (the fp16 presets return fp16 host tensors):
+        # resample in fp32 and round once
+        return F.interpolate(img.float(), size=tuple(size), mode=mode, align_corners=False, antialias=True).to(img.dtype)
     return F.interpolate(img, size=tuple(size), mode=mode, align_corners=False, antialias=True)
 
 

@@ -291,6 +291,16 @@ def _case(g, tag):
     return N, H, W, w, iters, G, dil, snips
 
 
+@pytest.fixture(params=[-1, 0, 1, 2, 3, 4], ids=lambda c: f"cfg{c}")
+def coalign_cfg(request):
+    """Every organisation of the optimisation pass (include/rd_b200.h rd_coalign_set_config): -1 automatic,
+    0 / 1 pixel-packed kernel, 2 / 3 / 4 contribution-packed kernel."""
+    from rollingdepth_b200 import _lib as L
+    assert L.lib().rd_coalign_set_config(request.param) >= 1
+    yield request.param
+    L.lib().rd_coalign_set_config(-1)
+
+
 @pytest.mark.parametrize("tag", ["a", "b", "h", "w2"])
 def test_min_and_prep_bit_exact(golden_dir, tag):
     from rollingdepth_b200.depth_aligner import DepthAligner
@@ -308,7 +318,7 @@ def test_min_and_prep_bit_exact(golden_dir, tag):
 
 
 @pytest.mark.parametrize("tag", ["a", "b", "h", "w2"])
-def test_coalign_teacher_forced_one_iteration(golden_dir, tag):
+def test_coalign_teacher_forced_one_iteration(golden_dir, tag, coalign_cfg):
     """Load the reference's (s, t, m, v, step) at iteration k, run ONE of our iterations, compare the
     new parameters with the reference's own autograd + torch.optim.Adam result and the loss entry."""
     from rollingdepth_b200.depth_aligner import DepthAligner
@@ -339,7 +349,7 @@ def test_coalign_teacher_forced_one_iteration(golden_dir, tag):
 
 
 @pytest.mark.parametrize("tag", ["a", "b", "w2"])
-def test_coalign_free_run_matches_reference_history(golden_dir, tag):
+def test_coalign_free_run_matches_reference_history(golden_dir, tag, coalign_cfg):
     from rollingdepth_b200.depth_aligner import DepthAligner
     dev = _dev()
     g = _load(golden_dir, "coalign.npz")
@@ -391,7 +401,7 @@ def test_renorm_bit_exact(dtype):
     assert torch.equal(out, ref)
 
 
-def test_coalign_fast_preset_size_vs_oracle():
+def test_coalign_fast_preset_size_vs_oracle(coalign_cfg):
     """N = 150 frames at 432x768 fp16, dilations [1, 25] (the `fast` preset's aligner problem):
     three iterations against the CPU oracle + invariants at full size."""
     from rollingdepth_b200.depth_aligner import DepthAligner
@@ -415,6 +425,30 @@ def test_coalign_fast_preset_size_vs_oracle():
     merged = al.merge(pb, dsn, dev_min, torch.ones_like(state[0]), torch.zeros_like(state[1])).cpu()
     ref = oc.merge(shifted, [torch.ones(n) for n in (148, 100)], [torch.zeros(n) for n in (148, 100)], dil, N)
     assert torch.equal(merged, ref)
+
+
+def test_coalign_multi_chunk_frames_vs_oracle(coalign_cfg):
+    """1024x576 fp32 with three dilations (R = 9 contributions, P = 5916 subsampled pixels): every frame is split into
+    several chunks, so the cross-chunk hand-over (ticket, last chunk finalises the frame) and the boundary frames with
+    absent contributions are exercised; three iterations against the CPU oracle, and two runs must agree bit for bit."""
+    from rollingdepth_b200.depth_aligner import DepthAligner
+    from oracle.gen_golden import synth_snippets
+    dev = _dev()
+    N, H, W, w, dil = 24, 576, 1024, 3, [1, 4, 9]
+    snips = synth_snippets(N, H, W, w, dil, seed=5)
+    al = DepthAligner(device=dev, num_iterations=3)
+    pb, dsn, dev_min, x_small = al.prepare(snips, dil)
+    assert pb.P == 58 * 102
+    state = al.new_state(pb)
+    hist = al.optimize_state(pb, x_small, state, 0, 3).cpu().numpy()
+    state2 = al.new_state(pb)
+    hist2 = al.optimize_state(pb, x_small, state2, 0, 3).cpu().numpy()
+    assert all(torch.equal(a, b) for a, b in zip(state, state2)) and np.array_equal(hist, hist2)
+    _, _, small = oc.prep(snips)
+    s_ls, t_ls, ohist, _ = oc.optimize(small, dil, N, num_iterations=3)
+    np.testing.assert_allclose(hist, np.array(ohist), rtol=2e-5, atol=2e-6)
+    assert float(((state[0].cpu() - torch.cat(s_ls)).abs() / torch.cat(s_ls).abs()).max()) <= 1e-4
+    assert float((state[1].cpu() - torch.cat(t_ls)).abs().max()) <= 1e-4
 
 
 def test_coalign_recovers_known_affine():
