@@ -139,7 +139,8 @@ typedef struct rd_coalign_hparams {
 
 /* Kernel organisation of the optimisation pass (A/B measurements and the parity tests, which run all of them):
  * -1 = chosen per problem (default), 0 / 1 = pixel-packed kernel with 192 x 2 / 128 x 3 CTAs per SM,
- * 2 / 3 / 4 = contribution-packed kernel with 128 x 4 / 256 x 2 / 512 x 1 CTAs per SM.  Call before rd_coalign_workspace_bytes:
+ * 2 / 3 / 4 = contribution-packed kernel with 128 x 4 / 256 x 2 / 512 x 1 CTAs per SM, 5 / 6 = frame-persistent
+ * contribution-packed kernel (one CTA per frame, two-stage ring) with 128 x 4 / 256 x 2.  Call before rd_coalign_workspace_bytes:
  * the workspace layout depends on it.  Returns the previous setting + 2 (>= 1), or a negative rd_status. */
 int rd_coalign_set_config(int cfg);
 

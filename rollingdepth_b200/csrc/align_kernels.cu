@@ -905,6 +905,291 @@ __global__ void __launch_bounds__(kPassThreads, kCtasPerSm) coalign_pass_cp_kern
     }
 }
 
+// Frame-persistent variant of the contribution-packed pass (cfg 5): ONE CTA per frame walks the frame's chunks through a
+// two-stage shared-memory ring (the bulk copies of chunk c + 2 are issued as soon as chunk c has been consumed) and keeps
+// its accumulators in registers across chunks.  Per frame instead of per (frame, chunk): one parameter prologue, one
+// block reduction, no partial sums in global memory, no ticket and no fences.  With ~1400-pixel chunks the per-chunk
+// reduction and prologue were a quarter of the instructions of the chunked kernels.
+template <typename T, int RH, int kPassThreads, int kCtasPerSm>
+__global__ void __launch_bounds__(kPassThreads, kCtasPerSm) coalign_pass_fp_kernel(const PassParams p) {
+    constexpr int RM = 2 * RH;
+    constexpr int NV = 4 * RM + kFrameStats;
+    constexpr int NROUND = (4 * RM + 4 + 31) / 32;       // summed values: 4 per contribution + fa, fb, l1, l2
+    extern __shared__ __align__(128) unsigned char pass_smem[];
+    __shared__ int sh_row[RM];
+    __shared__ float sh_s[RM], sh_t[RM], sh_soft[RM];
+    __shared__ float sh_red[kPassThreads / 32][NROUND * 32 + 2];
+    __shared__ float sh_tot[NV];
+
+    const int tid = threadIdx.x;
+    const int f = p.f_begin + blockIdx.x;
+    const int ch = 0;                                             // one CTA owns the whole frame
+    const int R = p.R, nt = p.n_total;
+    const int pitch = p.px_per_chunk;
+    const int nchunk = p.C;
+    __shared__ __align__(8) uint64_t sh_full[2];
+    T* stage0 = reinterpret_cast<T*>(pass_smem);                  // two stages of [RM][pitch]
+    const size_t stage_elems = (size_t)RM * pitch;
+
+    // bulk copies of chunk `c` into stage c & 1 (thread 0): the rows of the contributions that exist for this frame
+    auto issue_chunk = [&](int c) {
+        const int px0 = c * pitch;
+        const int npx = min(p.P_pad, px0 + pitch) - px0;          // multiple of 8
+        T* st = stage0 + (size_t)(c & 1) * stage_elems;
+        uint64_t* bar = &sh_full[c & 1];
+        uint32_t total = 0;
+        for (int cc = 0; cc < R; ++cc) {
+            const int g = cc / p.w, j = cc - g * p.w;
+            const int k = f - j * p.d[g];
+            if (k >= 0 && k < p.n[g]) total += (uint32_t)(npx * sizeof(T));
+        }
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pass_smem_u32(bar)), "r"(total) : "memory");
+        for (int cc = 0; cc < R; ++cc) {
+            const int g = cc / p.w, j = cc - g * p.w;
+            const int k = f - j * p.d[g];
+            if (k >= 0 && k < p.n[g]) {
+                const T* src = reinterpret_cast<const T*>(p.x) + ((size_t)(p.row0[g] + k) * p.w + j) * p.P_pad + px0;
+                bulk_g2s(st + (size_t)cc * pitch, src, (uint32_t)(npx * sizeof(T)), bar);
+            }
+        }
+    };
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pass_smem_u32(&sh_full[0])) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(pass_smem_u32(&sh_full[1])) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        issue_chunk(0);
+        if (nchunk > 1) issue_chunk(1);
+    }
+
+    // ---------------- prologue: parameters of the <= R snippets touching this frame (overlaps the copies)
+    if (tid >= 32 && tid < 32 + RM) {
+        const int c = tid - 32;
+        int row = -1;
+        float s = 0.f, t = 0.f, soft = 0.f;
+        if (c < R) {
+            const int g = c / p.w, j = c - g * p.w;
+            const int d = p.d[g];
+            const int k = f - j * d;
+            if (k >= 0 && k < p.n[g]) {
+                row = p.row0[g] + k;
+                s = __ldcg(p.theta_in + row);
+                t = __ldcg(p.theta_in + nt + row);
+                const float ng = (float)p.n[g];
+                if (p.apply_update) {
+                    float ms = __ldcg(p.theta_in + 2 * nt + row), mt = __ldcg(p.theta_in + 3 * nt + row);
+                    float vs = __ldcg(p.theta_in + 4 * nt + row), vt = __ldcg(p.theta_in + 5 * nt + row);
+                    float gs = 0.f, gt = 0.f;
+                    for (int jj = 0; jj < p.w; ++jj) {
+                        const int fp = k + jj * d;
+                        const float2 gg = __ldcg(reinterpret_cast<const float2*>(p.gterm_in) + (size_t)fp * R + g * p.w + jj);
+                        gs += gg.x;
+                        gt += gg.y;
+                    }
+                    gs += -2.f * p.lmda2 * fmaxf(1.f - s, 0.f) / ng;
+                    gt += 2.f * p.lmda3 * t / ng;
+                    adam_update(s, ms, vs, gs, p);
+                    adam_update(t, mt, vt, gt, p);
+                    if (ch == 0) {
+                        // every frame touching this snippet writes the same bits (deterministic recompute)
+                        p.theta_out[row] = s;           p.theta_out[nt + row] = t;
+                        p.theta_out[2 * nt + row] = ms; p.theta_out[3 * nt + row] = mt;
+                        p.theta_out[4 * nt + row] = vs; p.theta_out[5 * nt + row] = vt;
+                    }
+                }
+                if (j == 0) {
+                    const float hinge = fmaxf(1.f - s, 0.f);
+                    soft = (p.lmda2 * hinge * hinge + p.lmda3 * t * t) / ng;
+                }
+            }
+        }
+        sh_row[c] = row;
+        sh_s[c] = row >= 0 ? s : 0.f;       // absent contribution: y = 0 * 0 + 0 (below the clip => no gradient either)
+        sh_t[c] = row >= 0 ? t : 0.f;
+        sh_soft[c] = soft;
+    }
+    __syncthreads();
+    if (ch == 0 && tid == 0) {
+        float soft = 0.f;
+        for (int c = 0; c < R; ++c) soft += sh_soft[c];
+        p.hist_frame[(size_t)f * 4 + 1] = soft;
+    }
+
+    uint64_t sc2[RH], tc2[RH], vm2[RH];
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < RH; ++i) {
+        const bool v0 = sh_row[i] >= 0, v1 = sh_row[i + RH] >= 0;
+        sc2[i] = pk2(sh_s[i], sh_s[i + RH]);
+        tc2[i] = pk2(sh_t[i], sh_t[i + RH]);
+        vm2[i] = pk2(v0 ? 1.f : 0.f, v1 ? 1.f : 0.f);
+        cnt += (int)v0 + (int)v1;
+    }
+    const float cntf = (float)cnt;
+    const float rcnt = __fdiv_rn(1.f, cntf);
+    const bool single = cnt <= 1;       // y == target exactly: the data term has zero gradient (sign(0) = 0)
+    if (cnt != RM) {                    // CTA-uniform: zero-fill the rows of absent contributions in both stages (x = 0)
+        for (int c = 0; c < 2 * RM; ++c) {
+            if (sh_row[c % RM] >= 0) continue;
+            uint4* z = reinterpret_cast<uint4*>(stage0 + (size_t)(c / RM) * stage_elems + (size_t)(c % RM) * pitch);
+            for (int q = tid; q < (int)(pitch * sizeof(T) / 16); q += kPassThreads) z[q] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();
+    }
+
+    PassAccC<RH> acc;
+#pragma unroll
+    for (int i = 0; i < RH; ++i) { acc.A0[i] = acc.A1[i] = acc.D0[i] = acc.D1[i] = 0ull; }
+    acc.l1 = 0ull;
+    acc.l2 = acc.fa = acc.fb = 0.f;
+    acc.tmin = INFINITY;
+    acc.tmax = -INFINITY;
+    for (int c = 0; c < nchunk; ++c) {
+    {   // wait for chunk c (its stage is used for the (c >> 1)-th time)
+        uint32_t ok = 0;
+        int spins = 0;
+        do {
+            asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2, 100000;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                         : "=r"(ok) : "r"(pass_smem_u32(&sh_full[c & 1])), "r"((uint32_t)((c >> 1) & 1)) : "memory");
+            if (!ok && ++spins > 4000000) __trap();
+        } while (!ok);
+    }
+    const T* stage = stage0 + (size_t)(c & 1) * stage_elems;
+    const T* hi_rows = stage + (size_t)RH * pitch;
+    const int px0 = c * pitch;
+    const int nvalid = min(p.P, px0 + pitch) - px0;               // real pixels of this chunk
+    for (int q = tid; q < nvalid; q += kPassThreads) {
+        uint64_t xv[RH], iv[RH];
+        uint64_t sy2 = 0ull, si2 = 0ull;
+#pragma unroll
+        for (int i = 0; i < RH; ++i) {
+            xv[i] = lds_two_rows<T>(stage + (size_t)i * pitch + q, hi_rows + (size_t)i * pitch + q);
+            const uint64_t y = ffma2(sc2[i], xv[i], tc2[i]);
+            float y0, y1;
+            upk2(y, y0, y1);
+            iv[i] = pk2(rcp_fast(fmaxf(y0, 1e-3f)), rcp_fast(fmaxf(y1, 1e-3f)));
+            sy2 = ffma2(y, vm2[i], sy2);
+            si2 = ffma2(iv[i], vm2[i], si2);
+        }
+        float sya, syb, sia, sib;
+        upk2(sy2, sya, syb);
+        upk2(si2, sia, sib);
+        const float sy = sya + syb, si = sia + sib;
+        // target = sum / cnt: reciprocal product + one Newton step (correctly rounded quotient)
+        float tg = sy * rcnt, td = si * rcnt;
+        tg = fmaf(fmaf(-cntf, tg, sy), rcnt, tg);
+        td = fmaf(fmaf(-cntf, td, si), rcnt, td);
+        acc.fa += fabsf(tg);
+        acc.fb += fabsf(td);
+        acc.tmin = fminf(acc.tmin, tg);
+        acc.tmax = fmaxf(acc.tmax, tg);
+        if (single) continue;           // CTA-uniform
+        const uint64_t tg2 = bc2(tg), td2 = bc2(td);
+#pragma unroll
+        for (int i = 0; i < RH; ++i) {
+            const uint64_t x = xv[i];
+            const uint64_t y = ffma2(sc2[i], x, tc2[i]);
+            const uint64_t r1 = fsub2(y, tg2);
+            float v0, v1;
+            upk2(vm2[i], v0, v1);
+            const uint64_t sg = signed_mag2(v0, v1, r1);                          // sign(y - target), 0 where absent
+            acc.l1 = ffma2(sg, r1, acc.l1);                                        // |r1|
+            acc.A0[i] = fadd2(acc.A0[i], sg);
+            acc.A1[i] = ffma2(sg, x, acc.A1[i]);
+            const uint64_t in = iv[i];
+            const uint64_t r2 = fsub2(in, td2);
+            float y0, y1, q0f, q1f;
+            upk2(y, y0, y1);
+            upk2(r2, q0f, q1f);
+            acc.l2 = fmaf(fabsf(q0f), v0, acc.l2);
+            acc.l2 = fmaf(fabsf(q1f), v1, acc.l2);
+            // d(1/clamp(y, 1e-3))/dy = -1/y^2 where y >= 1e-3, else 0; absent contributions have y = 0 < 1e-3
+            const uint64_t sm = signed_mag2(y0 >= 1e-3f ? 1.0f : 0.0f, y1 >= 1e-3f ? 1.0f : 0.0f, r2);
+            const uint64_t w = fmul2(in, in);
+            acc.D0[i] = ffma2(sm, w, acc.D0[i]);
+            acc.D1[i] = ffma2(sm, fmul2(w, x), acc.D1[i]);
+        }
+    }
+
+    __syncthreads();                                              // every thread is done reading stage c & 1
+    if (tid == 0 && c + 2 < nchunk) issue_chunk(c + 2);
+    }
+
+    // ---------------- block reduction: butterfly within warps, fixed-order sum across warps
+    const int lane = tid & 31, warp = tid >> 5;
+    {
+        float slot[NROUND][32];
+#pragma unroll
+        for (int r = 0; r < NROUND; ++r)
+#pragma unroll
+            for (int i = 0; i < 32; ++i) slot[r][i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < RH; ++i) {
+            float lo, hi;
+            const int c0 = i, c1 = i + RH;
+            upk2(acc.A0[i], lo, hi); slot[(4 * c0 + 0) / 32][(4 * c0 + 0) % 32] = lo; slot[(4 * c1 + 0) / 32][(4 * c1 + 0) % 32] = hi;
+            upk2(acc.A1[i], lo, hi); slot[(4 * c0 + 1) / 32][(4 * c0 + 1) % 32] = lo; slot[(4 * c1 + 1) / 32][(4 * c1 + 1) % 32] = hi;
+            upk2(acc.D0[i], lo, hi); slot[(4 * c0 + 2) / 32][(4 * c0 + 2) % 32] = lo; slot[(4 * c1 + 2) / 32][(4 * c1 + 2) % 32] = hi;
+            upk2(acc.D1[i], lo, hi); slot[(4 * c0 + 3) / 32][(4 * c0 + 3) % 32] = lo; slot[(4 * c1 + 3) / 32][(4 * c1 + 3) % 32] = hi;
+        }
+        float l1a, l1b;
+        upk2(acc.l1, l1a, l1b);
+        slot[(4 * RM + 0) / 32][(4 * RM + 0) % 32] = acc.fa;
+        slot[(4 * RM + 1) / 32][(4 * RM + 1) % 32] = acc.fb;
+        slot[(4 * RM + 2) / 32][(4 * RM + 2) % 32] = l1a + l1b;
+        slot[(4 * RM + 3) / 32][(4 * RM + 3) % 32] = acc.l2;
+#pragma unroll
+        for (int r = 0; r < NROUND; ++r) {
+            const float tot = warp_transpose_sum<32>(slot[r], lane);
+            sh_red[warp][r * 32 + lane] = tot;
+        }
+        const float mn = warp_min(acc.tmin), mx = warp_max(acc.tmax);
+        if (lane == 0) { sh_red[warp][NROUND * 32] = mn; sh_red[warp][NROUND * 32 + 1] = mx; }
+    }
+    __syncthreads();
+    if (tid < NV) {
+        // NV layout: [4*c + {A0,A1,D0,D1}] for c < RM, then fa, fb, l1, l2, tmin, tmax, pad, pad
+        const int q = tid - 4 * RM;
+        float v;
+        if (q == 4 || q == 5) {
+            v = sh_red[0][NROUND * 32 + (q - 4)];
+            for (int w = 1; w < kPassThreads / 32; ++w) {
+                const float o = sh_red[w][NROUND * 32 + (q - 4)];
+                v = (q == 4) ? fminf(v, o) : fmaxf(v, o);
+            }
+        } else if (q >= 6) {
+            v = 0.f;
+        } else {
+            v = 0.f;
+#pragma unroll
+            for (int w = 0; w < kPassThreads / 32; ++w) v += sh_red[w][tid];
+        }
+        sh_tot[tid] = v;
+    }
+    __syncthreads();
+
+    // ---------------- per-frame scales, gradient terms, loss term ----
+    const float a = sh_tot[4 * RM + 0] * p.inv_P;   // mean_p |target|   (depth_aligner.py:197)
+    const float b = sh_tot[4 * RM + 1] * p.inv_P;   // mean_p |target_depth|
+    const float ia = __fdiv_rn(1.f, a), ib = __fdiv_rn(1.f, b);
+    if (tid < R) {
+        float2 gg = make_float2(0.f, 0.f);
+        if (sh_row[tid] >= 0) {
+            const float a0 = sh_tot[4 * tid + 0], a1 = sh_tot[4 * tid + 1];
+            const float d0 = sh_tot[4 * tid + 2], d1 = sh_tot[4 * tid + 3];
+            gg.x = p.ls_over_Z * (a1 * ia - p.dlw * d1 * ib);   // d loss / d s  (data term)
+            gg.y = p.ls_over_Z * (a0 * ia - p.dlw * d0 * ib);   // d loss / d t
+        }
+        reinterpret_cast<float2*>(p.gterm_out)[(size_t)f * R + tid] = gg;
+    }
+    if (tid == 0) {
+        float* h = p.hist_frame + (size_t)f * 4;
+        h[0] = p.ls_over_Z * (sh_tot[4 * RM + 2] * ia + p.dlw * sh_tot[4 * RM + 3] * ib);
+        h[2] = sh_tot[4 * RM + 4];
+        h[3] = sh_tot[4 * RM + 5];
+    }
+}
+
+
 // final Adam update for snippets whose first frame lies in [f_begin, f_end)
 __global__ void coalign_final_update_kernel(PassParams p, int f_begin, int f_end, float* s, float* t, float* m_s,
                                             float* m_t, float* v_s, float* v_t) {
@@ -1125,12 +1410,12 @@ static int pick_rm(int R) {
 
 // working set of one iteration above which the subsampled snippets no longer stay in the 126 MB L2
 constexpr long long kPassL2Bytes = 100ll << 20;
-static int g_pass_cfg_forced = -2;       // -2: not read yet, -1: automatic, 0..4: forced (RD_COALIGN_CFG / rd_coalign_set_config)
+static int g_pass_cfg_forced = -2;       // -2: not read yet, -1: automatic, 0..6: forced (RD_COALIGN_CFG / rd_coalign_set_config)
 static int pass_cfg(const rd_coalign_problem* p) {
     if (g_pass_cfg_forced == -2) {
         const char* e = getenv("RD_COALIGN_CFG");
         g_pass_cfg_forced = e ? atoi(e) : -1;
-        if (g_pass_cfg_forced < -1 || g_pass_cfg_forced > 4) g_pass_cfg_forced = -1;
+        if (g_pass_cfg_forced < -1 || g_pass_cfg_forced > 6) g_pass_cfg_forced = -1;
     }
     if (g_pass_cfg_forced >= 0) return g_pass_cfg_forced;
     const long long bytes = (long long)p->n_total * p->w * p->P_pad * (p->dtype == RD_F32 ? 4 : 2);
@@ -1145,6 +1430,8 @@ static int pass_smem_budget(const rd_coalign_problem* p) {
         case 2: return 55 * 1024;
         case 3: return 110 * 1024;
         case 4: return 200 * 1024;
+        case 5: return 55 * 1024 / 2;        // cfg 5 / 6: frame-persistent kernel, two stages per CTA (128 x 4 / 256 x 2)
+        case 6: return 110 * 1024 / 2;
         default: return 98304;
     }
 }
@@ -1236,8 +1523,23 @@ static int launch_pass_cp(const PassParams& pp, dim3 grid, cudaStream_t st) {
     RD_LAUNCH_CHECK("coalign_pass_cp_kernel");
     return RD_OK;
 }
+template <typename T, int RH, int NT, int NCTA>
+static int launch_pass_fp(const PassParams& pp, int n_frames, cudaStream_t st) {
+    auto kern = coalign_pass_fp_kernel<T, RH, NT, NCTA>;
+    const int smem = 2 * 2 * RH * pp.px_per_chunk * (int)sizeof(T);
+    static PerDeviceOnce configured;      // cudaFuncSetAttribute is per device and not a stream operation
+    if (configured.needed()) {
+        RD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+        configured.done();
+    }
+    kern<<<n_frames, NT, smem, st>>>(pp);
+    RD_LAUNCH_CHECK("coalign_pass_fp_kernel");
+    return RD_OK;
+}
 template <typename T, int RH>
 static int launch_pass_cpk(const PassParams& pp, int cfg, dim3 grid, cudaStream_t st) {
+    if (cfg == 6) return launch_pass_fp<T, RH, 256, 2>(pp, (int)grid.y, st);
+    if (cfg == 5) return launch_pass_fp<T, RH, 128, 4>(pp, (int)grid.y, st);
     if (cfg == 4) return launch_pass_cp<T, RH, 512, 1>(pp, grid, st);
     if (cfg == 3) return launch_pass_cp<T, RH, 256, 2>(pp, grid, st);
     return launch_pass_cp<T, RH, 128, 4>(pp, grid, st);
@@ -1386,7 +1688,7 @@ int rd_coalign_prep(const void* const* host_snip_ptrs, const rd_coalign_problem*
 }
 
 int rd_coalign_set_config(int cfg) {
-    RD_CHECK_ARG(cfg >= -1 && cfg <= 4, "cfg must be -1 (automatic) or 0..4");
+    RD_CHECK_ARG(cfg >= -1 && cfg <= 6, "cfg must be -1 (automatic) or 0..6");
     (void)pass_cfg;                       // make sure the environment default has been read first
     if (g_pass_cfg_forced == -2) { rd_coalign_problem dummy{}; dummy.n_total = 1; dummy.w = 1; dummy.P_pad = 8; (void)pass_cfg(&dummy); }
     const int prev = g_pass_cfg_forced;

@@ -252,13 +252,12 @@ __global__ void __launch_bounds__(kGnMaxThreads) bias_residual_kernel(const AddP
             for (int i = 0; i < VN; ++i) add[i] += t[i];
         }
         const size_t base = (size_t)n * p.HW * p.C + cv * VN;
-        for (int row = row0 + r; row < row1; row += p.R) {
-            const size_t off = base + (size_t)row * p.C;
+        auto emit = [&](const uint4& xin, const uint4& rin, size_t off) {
             float f[VN];
-            gn_unpack<T>(ldg_stream16(reinterpret_cast<const T*>(p.x) + off), f);
+            gn_unpack<T>(xin, f);
             if (p.res) {
                 float g[VN];
-                gn_unpack<T>(ldg_stream16(reinterpret_cast<const T*>(p.res) + off), g);
+                gn_unpack<T>(rin, g);
 #pragma unroll
                 for (int i = 0; i < VN; ++i) f[i] += g[i];
             }
@@ -266,6 +265,30 @@ __global__ void __launch_bounds__(kGnMaxThreads) bias_residual_kernel(const AddP
 #pragma unroll
             for (int i = 0; i < VN; ++i) o[i] = Cvt<T>::from_f(f[i] + add[i]);
             *reinterpret_cast<uint4*>(reinterpret_cast<T*>(p.y) + off) = *reinterpret_cast<const uint4*>(o);
+        };
+        int row = row0 + r;
+        // four rows per trip: up to eight independent 16-byte loads in flight per thread before the first store
+        for (; row + 3 * p.R < row1; row += 4 * p.R) {
+            size_t off[4];
+            uint4 xin[4], rin[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                off[u] = base + (size_t)(row + u * p.R) * p.C;
+                xin[u] = ldg_stream16(reinterpret_cast<const T*>(p.x) + off[u]);
+            }
+            if (p.res) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) rin[u] = ldg_stream16(reinterpret_cast<const T*>(p.res) + off[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) emit(xin[u], rin[u], off[u]);
+        }
+        for (; row < row1; row += p.R) {
+            const size_t off = base + (size_t)row * p.C;
+            const uint4 xin = ldg_stream16(reinterpret_cast<const T*>(p.x) + off);
+            uint4 rin = xin;
+            if (p.res) rin = ldg_stream16(reinterpret_cast<const T*>(p.res) + off);
+            emit(xin, rin, off);
         }
     }
 }
@@ -419,7 +442,7 @@ int rd_bias_residual_nhwc(const void* x, const void* bias, const void* vec, cons
     while (p.CV % cvt) --cvt;
     int R = 256 / cvt; if (R < 1) R = 1; if (R > 32) R = 32;
     p.R = R;
-    int rows = 8 * R;
+    int rows = 16 * R;                    // 16 rows per thread: four trips of four rows
     int chunks = (HW + rows - 1) / rows;
     if (chunks > 4096) { chunks = 4096; rows = (HW + chunks - 1) / chunks; chunks = (HW + rows - 1) / rows; }
     p.chunks = chunks; p.rows_per_chunk = rows;

@@ -291,10 +291,10 @@ def _case(g, tag):
     return N, H, W, w, iters, G, dil, snips
 
 
-@pytest.fixture(params=[-1, 0, 1, 2, 3, 4], ids=lambda c: f"cfg{c}")
+@pytest.fixture(params=[-1, 0, 1, 2, 3, 4, 5, 6], ids=lambda c: f"cfg{c}")
 def coalign_cfg(request):
     """Every organisation of the optimisation pass (include/rd_b200.h rd_coalign_set_config): -1 automatic,
-    0 / 1 pixel-packed kernel, 2 / 3 / 4 contribution-packed kernel."""
+    0 / 1 pixel-packed kernel, 2 / 3 / 4 contribution-packed kernel, 5 / 6 frame-persistent contribution-packed kernel."""
     from rollingdepth_b200 import _lib as L
     assert L.lib().rd_coalign_set_config(request.param) >= 1
     yield request.param
