@@ -156,7 +156,6 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepParams pp, const float* d
 // shape 1: 128 threads x 3 CTAs/SM, 64 KB staged each (three-way overlap of the load / compute / reduce phases of
 //          consecutive CTAs: best when every iteration streams from HBM).  Chosen per problem by its working set;
 //          RD_COALIGN_CFG=0/1 forces one of them (A/B measurements).
-constexpr int kPassThreadsMax = 192;
 constexpr int kPassV = 2;                 // pixels per thread per step (one 4- or 8-byte shared-memory load)
 constexpr int kPassSmemBudgetMax = 98304;
 constexpr int kFrameStats = 8;            // sum|target|, sum|tdep|, L1, L2, tmin, tmax, pad, pad
@@ -928,6 +927,8 @@ __global__ void __launch_bounds__(kPassThreads, kCtasPerSm) coalign_pass_fp_kern
     const int pitch = p.px_per_chunk;
     const int nchunk = p.C;
     __shared__ __align__(8) uint64_t sh_full[2];
+    __shared__ const T* sh_src[RM];                              // global row start of every contribution (nullptr: absent)
+    __shared__ int sh_nrows;
     T* stage0 = reinterpret_cast<T*>(pass_smem);                  // two stages of [RM][pitch]
     const size_t stage_elems = (size_t)RM * pitch;
 
@@ -951,6 +952,20 @@ __global__ void __launch_bounds__(kPassThreads, kCtasPerSm) coalign_pass_fp_kern
                 const T* src = reinterpret_cast<const T*>(p.x) + ((size_t)(p.row0[g] + k) * p.w + j) * p.P_pad + px0;
                 bulk_g2s(st + (size_t)cc * pitch, src, (uint32_t)(npx * sizeof(T)), bar);
             }
+        }
+    };
+    // the same from the row pointers the prologue leaves in shared memory (a dozen instructions per row instead of the
+    // index arithmetic above: thread 0 is also a compute thread, and its warp is what the per-chunk barrier waits for)
+    auto issue_chunk_fast = [&](int c) {
+        const int px0 = c * pitch;
+        const uint32_t bytes = (uint32_t)((min(p.P_pad, px0 + pitch) - px0) * sizeof(T));
+        T* st = stage0 + (size_t)(c & 1) * stage_elems;
+        uint64_t* bar = &sh_full[c & 1];
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pass_smem_u32(bar)), "r"(bytes * (uint32_t)sh_nrows) : "memory");
+#pragma unroll 1
+        for (int cc = 0; cc < R; ++cc) {
+            const T* src = sh_src[cc];
+            if (src != nullptr) bulk_g2s(st + (size_t)cc * pitch, src + px0, bytes, bar);
         }
     };
     if (tid == 0) {
@@ -1003,6 +1018,10 @@ __global__ void __launch_bounds__(kPassThreads, kCtasPerSm) coalign_pass_fp_kern
             }
         }
         sh_row[c] = row;
+        {
+            const int g = c < R ? c / p.w : 0, j = c < R ? c - g * p.w : 0;
+            sh_src[c] = row >= 0 ? reinterpret_cast<const T*>(p.x) + ((size_t)row * p.w + j) * p.P_pad : nullptr;
+        }
         sh_s[c] = row >= 0 ? s : 0.f;       // absent contribution: y = 0 * 0 + 0 (below the clip => no gradient either)
         sh_t[c] = row >= 0 ? t : 0.f;
         sh_soft[c] = soft;
@@ -1024,6 +1043,7 @@ __global__ void __launch_bounds__(kPassThreads, kCtasPerSm) coalign_pass_fp_kern
         vm2[i] = pk2(v0 ? 1.f : 0.f, v1 ? 1.f : 0.f);
         cnt += (int)v0 + (int)v1;
     }
+    if (tid == 0) sh_nrows = cnt;       // read by thread 0 only
     const float cntf = (float)cnt;
     const float rcnt = __fdiv_rn(1.f, cntf);
     const bool single = cnt <= 1;       // y == target exactly: the data term has zero gradient (sign(0) = 0)
@@ -1111,7 +1131,7 @@ __global__ void __launch_bounds__(kPassThreads, kCtasPerSm) coalign_pass_fp_kern
     }
 
     __syncthreads();                                              // every thread is done reading stage c & 1
-    if (tid == 0 && c + 2 < nchunk) issue_chunk(c + 2);
+    if (tid == 0 && c + 2 < nchunk) issue_chunk_fast(c + 2);
     }
 
     // ---------------- block reduction: butterfly within warps, fixed-order sum across warps
@@ -1408,8 +1428,6 @@ static int pick_rm(int R) {
     return -1;
 }
 
-// working set of one iteration above which the subsampled snippets no longer stay in the 126 MB L2
-constexpr long long kPassL2Bytes = 100ll << 20;
 static int g_pass_cfg_forced = -2;       // -2: not read yet, -1: automatic, 0..6: forced (RD_COALIGN_CFG / rd_coalign_set_config)
 static int pass_cfg(const rd_coalign_problem* p) {
     if (g_pass_cfg_forced == -2) {
@@ -1418,8 +1436,13 @@ static int pass_cfg(const rd_coalign_problem* p) {
         if (g_pass_cfg_forced < -1 || g_pass_cfg_forced > 6) g_pass_cfg_forced = -1;
     }
     if (g_pass_cfg_forced >= 0) return g_pass_cfg_forced;
-    const long long bytes = (long long)p->n_total * p->w * p->P_pad * (p->dtype == RD_F32 ? 4 : 2);
-    return bytes > kPassL2Bytes ? 1 : 0;
+    // measured on B200 (tools/microbench.py align, profiles/r2_coalign_configs.txt):
+    //   short clips (about one CTA per SM: the launch is latency-bound, 12.5 us whatever the organisation) -> cfg 0;
+    //   long clips, fp32 snippets: frame-persistent contribution-packed kernel (cfg 5: 31.3 / 90.1 us per iteration on
+    //   the 77 MB / 208 MB problems against 35.4 / 99.6 for cfg 0); 16-bit snippets: chunked contribution-packed
+    //   kernel (cfg 2: 26.9 us against 35.1).
+    if (p->N <= 2 * num_sms()) return 0;
+    return p->dtype == RD_F32 ? 5 : 2;
 }
 // cfg 0 / 1: pixel-packed kernel (192 x 2 / 128 x 3 CTAs per SM); cfg 2 / 3: contribution-packed kernel (128 x 4 / 256 x 2);
 // cfg 4: contribution-packed, one 512-thread CTA per SM (short clips: about one frame per SM, the launch is latency-bound
