@@ -20,6 +20,10 @@ except Exception as e:
     print(sys.argv[1], 'unreadable', e)
 PY
 }
+if has mtest; then
+  ( timeout 900 python -m pytest tests/test_gpu_multi.py -q -m gpu -p no:cacheprovider -k "[$N]" > gpurun_out/pytest_multi_$T.log 2>&1; echo "pytest exit=$?" >> gpurun_out/pytest_multi_$T.log )
+  grep -E "passed|failed|rror|exit=" gpurun_out/pytest_multi_$T.log | tail -5
+fi
 if has tests; then
   ( timeout 1500 python -m pytest tests/test_gpu_pipeline.py tests/test_video_call.py tests/test_gpu_multi.py -q -m gpu -p no:cacheprovider -s > gpurun_out/pytest_multi_$T.log 2>&1; echo "pytest exit=$?" >> gpurun_out/pytest_multi_$T.log )
   grep -E "cfg1:|fp16:|passed|failed|rror|exit=" gpurun_out/pytest_multi_$T.log | tail -12
