@@ -165,6 +165,7 @@ struct PassParams {
     int G, w, N, P, P_pad, R, C, n_total, px_per_chunk;
     int d[RD_MAX_GROUPS], n[RD_MAX_GROUPS], row0[RD_MAX_GROUPS];
     int f_begin;
+    int pdl;                 // host-side only: launch with programmatic stream serialization (see launch_pass_kernel)
     int apply_update;
     float step_size, bc2_sqrt, beta1, beta2, eps;
     float lmda2, lmda3, dlw, ls_over_Z, inv_P;
@@ -362,6 +363,7 @@ __global__ void __launch_bounds__(kPassThreads, kCtasPerSm) coalign_pass_kernel(
     __shared__ int sh_last;
 
     const int tid = threadIdx.x;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // let the next pass start its x loads early
     const int ch = blockIdx.x;
     const int f = p.f_begin + blockIdx.y;
     const int R = p.R, nt = p.n_total;
@@ -390,6 +392,10 @@ __global__ void __launch_bounds__(kPassThreads, kCtasPerSm) coalign_pass_kernel(
             }
         }
     }
+
+    // programmatic dependent launch: everything above touches only x (constant over the iterations) and may run while the
+    // previous pass is still finishing; everything below reads or writes what the previous pass wrote
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // ---------------- prologue: parameters of the <= R snippets touching this frame (overlaps the copies)
     if (tid >= 32 && tid < 32 + RM) {
@@ -628,6 +634,7 @@ __global__ void __launch_bounds__(kPassThreads, kCtasPerSm) coalign_pass_cp_kern
     __shared__ int sh_last;
 
     const int tid = threadIdx.x;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // let the next pass start its x loads early
     const int ch = blockIdx.x;
     const int f = p.f_begin + blockIdx.y;
     const int R = p.R, nt = p.n_total;
@@ -657,6 +664,10 @@ __global__ void __launch_bounds__(kPassThreads, kCtasPerSm) coalign_pass_cp_kern
             }
         }
     }
+
+    // programmatic dependent launch: everything above touches only x (constant over the iterations) and may run while the
+    // previous pass is still finishing; everything below reads or writes what the previous pass wrote
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // ---------------- prologue: parameters of the <= R snippets touching this frame (overlaps the copies)
     if (tid >= 32 && tid < 32 + RM) {
@@ -921,6 +932,7 @@ __global__ void __launch_bounds__(kPassThreads, kCtasPerSm) coalign_pass_fp_kern
     __shared__ float sh_tot[NV];
 
     const int tid = threadIdx.x;
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // let the next pass start its x loads early
     const int f = p.f_begin + blockIdx.x;
     const int ch = 0;                                             // one CTA owns the whole frame
     const int R = p.R, nt = p.n_total;
@@ -975,6 +987,10 @@ __global__ void __launch_bounds__(kPassThreads, kCtasPerSm) coalign_pass_fp_kern
         issue_chunk(0);
         if (nchunk > 1) issue_chunk(1);
     }
+
+    // programmatic dependent launch: everything above touches only x (constant over the iterations) and may run while the
+    // previous pass is still finishing; everything below reads or writes what the previous pass wrote
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     // ---------------- prologue: parameters of the <= R snippets touching this frame (overlaps the copies)
     if (tid >= 32 && tid < 32 + RM) {
@@ -1514,6 +1530,24 @@ static WsLayout ws_layout(const rd_coalign_problem* p, int n_iter) {
 
 struct WsFlags { int single_rank; int n_iter; };
 
+// Launch of one optimisation pass.  `pdl`: programmatic dependent launch -- the pass may begin (bulk loads of x, which no
+// pass writes) while the previous pass of the same stream is still running; its griddepcontrol.wait orders everything
+// else after the previous pass has completed and flushed.  Only passes that directly follow another pass use it.
+template <typename K>
+static cudaError_t launch_pass_kernel(K kern, dim3 grid, int threads, size_t smem, cudaStream_t st, bool pdl, const PassParams& pp) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, pp);
+}
+
 template <typename T, int RM, int NT, int NCTA>
 static int launch_pass_c(const PassParams& pp, dim3 grid, cudaStream_t st) {
     auto kern = coalign_pass_kernel<T, RM, NT, NCTA>;
@@ -1523,7 +1557,7 @@ static int launch_pass_c(const PassParams& pp, dim3 grid, cudaStream_t st) {
         RD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPassSmemBudgetMax + 1024));
         configured.done();
     }
-    kern<<<grid, NT, smem, st>>>(pp);
+    RD_CUDA(launch_pass_kernel(kern, grid, NT, (size_t)smem, st, pp.pdl != 0, pp));
     RD_LAUNCH_CHECK("coalign_pass_kernel");
     return RD_OK;
 }
@@ -1542,7 +1576,7 @@ static int launch_pass_cp(const PassParams& pp, dim3 grid, cudaStream_t st) {
         RD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, NCTA == 1 ? 204 * 1024 : 112 * 1024));
         configured.done();
     }
-    kern<<<grid, NT, smem, st>>>(pp);
+    RD_CUDA(launch_pass_kernel(kern, grid, NT, (size_t)smem, st, pp.pdl != 0, pp));
     RD_LAUNCH_CHECK("coalign_pass_cp_kernel");
     return RD_OK;
 }
@@ -1555,7 +1589,7 @@ static int launch_pass_fp(const PassParams& pp, int n_frames, cudaStream_t st) {
         RD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
         configured.done();
     }
-    kern<<<n_frames, NT, smem, st>>>(pp);
+    RD_CUDA(launch_pass_kernel(kern, dim3((unsigned)n_frames), NT, (size_t)smem, st, pp.pdl != 0, pp));
     RD_LAUNCH_CHECK("coalign_pass_fp_kernel");
     return RD_OK;
 }
@@ -1751,11 +1785,12 @@ int rd_coalign_begin(const rd_coalign_problem* p, const float* s, const float* t
 }
 
 static int pass_impl(const void* x_small, const rd_coalign_problem* p, const rd_coalign_hparams* hp, int it, int step0,
-                     int f_begin, int f_end, void* workspace, void* stream, bool single, int n_iter_layout) {
+                     int f_begin, int f_end, void* workspace, void* stream, bool single, int n_iter_layout, bool pdl = false) {
     const WsLayout L = ws_layout(p, n_iter_layout);
     PassParams pp{};
     pp.x = x_small;
     pp.f_begin = f_begin;
+    pp.pdl = pdl ? 1 : 0;
     fill_pass_params(pp, p, hp, L, reinterpret_cast<char*>(workspace), it, step0 + it, single);
     dim3 grid(L.C, f_end - f_begin);
     cudaStream_t st = (cudaStream_t)stream;
@@ -1818,8 +1853,11 @@ int rd_coalign_optimize(const void* x_small, const rd_coalign_problem* p, const 
     if (int e = check_problem(p)) return e;
     RD_CHECK_ARG(x_small && hp, "NULL pointer");
     if (int e = rd_coalign_begin(p, s, t, m_s, m_t, v_s, v_t, n_iter, 1, workspace, workspace_bytes, stream)) return e;
+    static int pdl_env = -1;             // RD_COALIGN_PDL=0 disables the programmatic dependent launches (A/B)
+    if (pdl_env < 0) { const char* e = getenv("RD_COALIGN_PDL"); pdl_env = e ? (atoi(e) != 0) : 1; }
     for (int it = 0; it < n_iter; ++it) {
-        if (int e = pass_impl(x_small, p, hp, it, step0, 0, p->N, workspace, stream, true, n_iter)) return e;
+        // pass `it` directly follows pass `it - 1` in the stream: it may start loading x while that one drains
+        if (int e = pass_impl(x_small, p, hp, it, step0, 0, p->N, workspace, stream, true, n_iter, pdl_env && it > 0)) return e;
     }
     return rd_coalign_end(p, hp, n_iter, step0, 0, p->N, s, t, m_s, m_t, v_s, v_t, history, workspace, stream);
 }
