@@ -229,6 +229,13 @@ int rd_upsample_nearest_nhwc(const void* x, void* y, int N, int Hi, int Wi, int 
  * (erf) GELU, rounding as torch (gelu in fp32 -> dtype, product in fp32 -> dtype).  One pass instead of gelu + mul. */
 int rd_geglu(const void* proj, void* y, int64_t M, int D, rd_dtype dtype, void* stream);
 
+/* Row softmax of the VAE mid-block attention (one head of dim 512; diffusers/src/diffusers/models/unets/unet_2d_blocks.py
+ * UNetMidBlock2D -> Attention -> F.scaled_dot_product_attention at attention_processor.py:2251): the fp32 logits come from a
+ * cuBLAS batched GEMM; out[r, :] = dtype(softmax(scale * logits[r, :])) in ONE pass (scale, softmax and the cast to the
+ * activation dtype were three element-wise passes over the [B, S, S] logits).  logits: contiguous [rows, cols] fp32,
+ * cols % 4 == 0 and cols <= 10240 (RD_ERR_UNSUPPORTED otherwise -- the caller keeps its library path); out: [rows, cols]. */
+int rd_softmax_rows(const float* logits, void* out, int64_t rows, int cols, float scale, rd_dtype out_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -167,3 +167,21 @@ def geglu(proj: torch.Tensor) -> torch.Tensor:
     L.call("rd_geglu", proj.device, L.ptr(proj), L.ptr(y), M, D, L.dtype_code(proj.dtype), L.stream_ptr(proj.device))
     L.count_launches(1)
     return y
+
+
+SOFTMAX_ROWS_MAX_COLS = 10240
+
+
+def softmax_rows(logits: torch.Tensor, scale: float, out_dtype: torch.dtype) -> torch.Tensor:
+    """softmax(scale * logits, dim=-1).to(out_dtype) for contiguous fp32 logits [..., cols] in one pass
+    (cols % 4 == 0, cols <= SOFTMAX_ROWS_MAX_COLS)."""
+    L.require_cuda(logits)
+    if logits.dtype != torch.float32 or not logits.is_contiguous():
+        raise L.RdError("softmax_rows expects contiguous float32 logits")
+    cols = logits.shape[-1]
+    rows = logits.numel() // cols
+    out = torch.empty(logits.shape, dtype=out_dtype, device=logits.device)
+    L.call("rd_softmax_rows", logits.device, L.ptr(logits), L.ptr(out), rows, cols, float(scale), L.dtype_code(out_dtype),
+           L.stream_ptr(logits.device))
+    L.count_launches(1)
+    return out

@@ -174,7 +174,12 @@ def _wide_head_attention(q, k, v):
     except (TypeError, RuntimeError):
         _GEMM_ATTENTION_OK = False
         return None
-    p = torch.softmax(logits.mul_(q.shape[-1] ** -0.5), dim=-1).to(q.dtype)
+    scale = q.shape[-1] ** -0.5
+    from .. import ops
+    if logits.shape[-1] % 4 == 0 and logits.shape[-1] <= ops.SOFTMAX_ROWS_MAX_COLS:
+        p = ops.softmax_rows(logits, scale, q.dtype)      # scale, softmax and cast in one pass over the fp32 logits
+    else:
+        p = torch.softmax(logits.mul_(scale), dim=-1).to(q.dtype)
     return torch.bmm(p, v2)[:, None]                      # [B, 1, Sq, d]
 
 

@@ -571,3 +571,47 @@ def test_geglu_matches_torch(dtype):
             # same operation order and roundings as torch: at most one ulp from erff differences
             ulp = 2.0 ** (-10 if dtype == torch.float16 else -7)
             assert float(((out.float() - ref.float()).abs() / ref.float().abs().clamp_min(1e-3)).max()) <= 2 * ulp
+
+
+# =============================================================================== VAE mid-block attention (head_dim 512)
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("rows,cols", [(7, 5184), (3, 9216), (33, 36), (2, 10240), (5, 1300)])
+def test_softmax_rows_matches_torch(rows, cols, dtype):
+    """rd_softmax_rows = torch.softmax(scale * logits, -1).to(dtype) in one pass (fp32 math, ex2.approx)."""
+    from rollingdepth_b200 import ops
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(rows * cols)
+    x = torch.randn(rows, cols, device=dev, generator=g) * 30.0
+    x[0, :4] = 200.0                                              # large logits: the row maximum must be subtracted
+    scale = 512 ** -0.5
+    y = ops.softmax_rows(x, scale, dtype)
+    ref = torch.softmax(x.double() * scale, dim=-1)
+    assert y.dtype == dtype and y.shape == x.shape
+    tol = {torch.float32: 2e-6, torch.float16: 6e-4, torch.bfloat16: 5e-3}[dtype]
+    assert float((y.double() - ref).abs().max()) <= tol
+    assert float((y.double().sum(-1) - 1).abs().max()) <= 50 * tol
+
+
+def test_softmax_rows_rejects_unsupported_rows():
+    from rollingdepth_b200 import ops, _lib as L
+    dev = _dev()
+    with pytest.raises(L.RdError):
+        ops.softmax_rows(torch.zeros(2, 10244, device=dev), 1.0, torch.float16)      # too many columns
+    with pytest.raises(L.RdError):
+        ops.softmax_rows(torch.zeros(2, 1302, device=dev), 1.0, torch.float16)       # not a multiple of 4
+
+
+@pytest.mark.parametrize("S", [336, 5184])
+def test_vae_mid_block_attention_matches_sdpa(S):
+    """The VAE mid-block attention (one head, head_dim 512) as run by the sd2 modules -- cuBLAS batched GEMM with fp32
+    logits, rd_softmax_rows, cuBLAS GEMM -- against F.scaled_dot_product_attention (the reference's call) on the same
+    q, k, v."""
+    from rollingdepth_b200.sd2 import layers as Ly
+    dev = _dev()
+    g = torch.Generator(device=dev).manual_seed(S)
+    q, k, v = [torch.randn(2, 1, S, 512, device=dev, dtype=torch.float16, generator=g) for _ in range(3)]
+    assert Ly._use_gemm_attention(q)
+    o = Ly._wide_head_attention(q, k, v)
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
+    assert o is not None and o.shape == q.shape
+    assert float((o.float() - ref).abs().max()) <= 5e-3
