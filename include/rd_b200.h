@@ -229,6 +229,14 @@ int rd_upsample_nearest_nhwc(const void* x, void* y, int N, int Hi, int Wi, int 
  * (erf) GELU, rounding as torch (gelu in fp32 -> dtype, product in fp32 -> dtype).  One pass instead of gelu + mul. */
 int rd_geglu(const void* proj, void* y, int64_t M, int D, rd_dtype dtype, void* stream);
 
+/* LayerNorm over the last axis of a contiguous [M, C] activation: the norm1 / norm2 / norm3 of every BasicTransformerBlock in front
+ * of the cross-frame attention, the text cross-attention and the feed-forward (diffusers/src/diffusers/models/attention.py:
+ * 447-448, 497-499, 520-521; torch.nn.functional.layer_norm).  Statistics in fp32 (two-pass), y = dtype(((x - mean) * rstd) *
+ * gamma + beta), one read and one write.  C % (16 / sizeof(dtype)) == 0 and C <= 2048 (fp16/bf16) / 1024 (fp32), else
+ * RD_ERR_UNSUPPORTED -- the caller keeps its library path. */
+int rd_layernorm(const void* x, void* y, const void* gamma, const void* beta, int64_t M, int C, float eps, rd_dtype dtype,
+                 void* stream);
+
 /* Row softmax of the VAE mid-block attention (one head of dim 512; diffusers/src/diffusers/models/unets/unet_2d_blocks.py
  * UNetMidBlock2D -> Attention -> F.scaled_dot_product_attention at attention_processor.py:2251): the fp32 logits come from a
  * cuBLAS batched GEMM; out[r, :] = dtype(softmax(scale * logits[r, :])) in ONE pass (scale, softmax and the cast to the

@@ -395,6 +395,68 @@ __global__ void __launch_bounds__(kSmThreads) softmax_rows_kernel(const float* _
     }
 }
 
+// LayerNorm over the last axis of a contiguous [M, C] activation (the three norms of every BasicTransformerBlock,
+// diffusers/src/diffusers/models/attention.py:447-448, 497-499, 520-521): one warp per row, the row lives in registers
+// (two-pass mean / variance in fp32 like torch), y = T(((x - mean) * rstd) * gamma + beta).  One read + one write.
+constexpr int kLnMaxVec = 8;          // 16-byte vectors per lane: C <= 32 * 8 * (16 / sizeof(T))
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(const T* __restrict__ x, T* __restrict__ y, const T* __restrict__ gamma,
+                                                             const T* __restrict__ beta, long long M, int C, float eps) {
+    constexpr int VN = GnVec<T>::N;
+    const int nv = C / VN, lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+    const float inv_c = 1.f / (float)C;
+    for (long long r = warp0; r < M; r += nwarps) {
+        const T* xr = x + r * C;
+        uint4 raw[kLnMaxVec];
+#pragma unroll
+        for (int k = 0; k < kLnMaxVec; ++k) {
+            const int i = lane + 32 * k;
+            if (i < nv) raw[k] = ldg_stream16(xr + (size_t)i * VN);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < kLnMaxVec; ++k) {
+            const int i = lane + 32 * k;
+            if (i < nv) {
+                float f[VN];
+                gn_unpack<T>(raw[k], f);
+#pragma unroll
+                for (int q = 0; q < VN; ++q) sum += f[q];
+            }
+        }
+        const float mean = warp_sum(sum) * inv_c;
+        float sq = 0.f;
+#pragma unroll
+        for (int k = 0; k < kLnMaxVec; ++k) {
+            const int i = lane + 32 * k;
+            if (i < nv) {
+                float f[VN];
+                gn_unpack<T>(raw[k], f);
+#pragma unroll
+                for (int q = 0; q < VN; ++q) { const float d = f[q] - mean; sq = fmaf(d, d, sq); }
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(sq) * inv_c + eps);
+        T* yr = y + r * C;
+#pragma unroll
+        for (int k = 0; k < kLnMaxVec; ++k) {
+            const int i = lane + 32 * k;
+            if (i < nv) {
+                float f[VN], g[VN], b[VN];
+                gn_unpack<T>(raw[k], f);
+                gn_unpack<T>(*reinterpret_cast<const uint4*>(gamma + (size_t)i * VN), g);
+                gn_unpack<T>(*reinterpret_cast<const uint4*>(beta + (size_t)i * VN), b);
+                alignas(16) T o[VN];
+#pragma unroll
+                for (int q = 0; q < VN; ++q) o[q] = Cvt<T>::from_f(fmaf((f[q] - mean) * rstd, g[q], b[q]));
+                *reinterpret_cast<uint4*>(yr + (size_t)i * VN) = *reinterpret_cast<const uint4*>(o);
+            }
+        }
+    }
+}
+
 static int gn_plan(GnParams& p, int es) {
     const int VN = 16 / es;
     // slice the channels over blockIdx.z until one pixel row of a slice fits one CTA (<= 512 vectors);
@@ -530,6 +592,28 @@ int rd_upsample_nearest_nhwc(const void* x, void* y, int N, int Hi, int Wi, int 
     const int blocks = (int)(want > (long long)num_sms() * 32 ? (long long)num_sms() * 32 : want);
     upsample_nearest_nhwc_kernel<uint4><<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
     RD_LAUNCH_CHECK("upsample_nearest_nhwc_kernel");
+    return RD_OK;
+}
+
+int rd_layernorm(const void* x, void* y, const void* gamma, const void* beta, int64_t M, int C, float eps, rd_dtype dtype,
+                 void* stream) {
+    RD_CHECK_ARG(x && y && gamma && beta && M >= 1 && C >= 1, "bad argument");
+    RD_CHECK_ARG(dtype == RD_F32 || dtype == RD_F16 || dtype == RD_BF16, "bad dtype");
+    const int es = dtype == RD_F32 ? 4 : 2, VN = 16 / es;
+    if (C % VN != 0 || C > 32 * kLnMaxVec * VN) {
+        set_error("C=%d: rd_layernorm needs a multiple of %d and at most %d channels", C, VN, 32 * kLnMaxVec * VN);
+        return RD_ERR_UNSUPPORTED;
+    }
+    RD_CHECK_ARG((((uintptr_t)x | (uintptr_t)y | (uintptr_t)gamma | (uintptr_t)beta) & 15) == 0, "pointers must be 16-byte aligned");
+    const long long want = (M + 7) / 8;
+    const int blocks = (int)(want > (long long)num_sms() * 8 ? (long long)num_sms() * 8 : want);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case RD_F32: layernorm_rows_kernel<float><<<blocks, 256, 0, st>>>((const float*)x, (float*)y, (const float*)gamma, (const float*)beta, M, C, eps); break;
+        case RD_F16: layernorm_rows_kernel<__half><<<blocks, 256, 0, st>>>((const __half*)x, (__half*)y, (const __half*)gamma, (const __half*)beta, M, C, eps); break;
+        default:     layernorm_rows_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, M, C, eps); break;
+    }
+    RD_LAUNCH_CHECK("layernorm_rows_kernel");
     return RD_OK;
 }
 

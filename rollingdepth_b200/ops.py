@@ -185,3 +185,26 @@ def softmax_rows(logits: torch.Tensor, scale: float, out_dtype: torch.dtype) -> 
            L.stream_ptr(logits.device))
     L.count_launches(1)
     return out
+
+
+def layer_norm_supported(x: torch.Tensor, C: int) -> bool:
+    vn = 16 // x.element_size()
+    return x.is_cuda and x.dtype in _LN_DTYPES and C % vn == 0 and C <= 32 * 8 * vn
+
+
+_LN_DTYPES = (torch.float16, torch.bfloat16, torch.float32)
+
+
+def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float) -> torch.Tensor:
+    """F.layer_norm(x, (C,), weight, bias, eps) over the last axis of a contiguous tensor in one pass."""
+    L.require_cuda(x)
+    if not x.is_contiguous():
+        x = x.contiguous()
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    y = torch.empty_like(x)
+    g, b = _opt(weight, x.dtype), _opt(bias, x.dtype)
+    L.call("rd_layernorm", x.device, L.ptr(x), L.ptr(y), L.ptr(g), L.ptr(b), M, Cc, float(eps), L.dtype_code(x.dtype),
+           L.stream_ptr(x.device))
+    L.count_launches(1)
+    return y

@@ -110,13 +110,15 @@ class RollingDepthPipeline:
         key = (self.device, self.dtype)
         if self._tuned_for == key:
             return
-        from .sd2.layers import BiasConv2d, GroupNormAct, ResnetBlock2D, Upsample2D
+        from .sd2.layers import BiasConv2d, GroupNormAct, LayerNormFused, ResnetBlock2D, Upsample2D
         for m in (self.unet, self.vae):
             if self.channels_last:
                 m.to(memory_format=torch.channels_last)
             for sub in m.modules():
                 if isinstance(sub, (GroupNormAct, BiasConv2d, ResnetBlock2D, Upsample2D)):
                     sub.fused = self.fused_norm and self.channels_last
+                elif isinstance(sub, LayerNormFused):
+                    sub.fused = self.fused_norm
         self._tuned_for = key
 
     # ------------------------------------------------------------------ optional per-stage device timing

@@ -615,3 +615,25 @@ def test_vae_mid_block_attention_matches_sdpa(S):
     ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
     assert o is not None and o.shape == q.shape
     assert float((o.float() - ref).abs().max()) <= 5e-3
+
+
+# =============================================================================== LayerNorm of the transformer blocks
+@pytest.mark.parametrize("dtype,tol", [(torch.float16, 2e-3), (torch.bfloat16, 1.6e-2), (torch.float32, 2e-6)])
+@pytest.mark.parametrize("M,C", [(1000, 320), (777, 640), (300, 1280), (5, 8), (33, 2048)])
+def test_layernorm_matches_torch_fp32(M, C, dtype, tol):
+    """Floating-point kernel: compared with F.layer_norm evaluated in fp32 on the same inputs; and with torch's own kernel in
+    the activation dtype (<= 1 ulp of the output)."""
+    from rollingdepth_b200 import ops
+    dev = _dev()
+    if dtype == torch.float32 and C > 1024:
+        pytest.skip("fp32 rows hold at most 1024 channels")
+    g = torch.Generator(device=dev).manual_seed(M + C)
+    x = (torch.randn(M, C, device=dev, generator=g) * 2 + torch.randn(M, 1, device=dev, generator=g) * 3).to(dtype)
+    w = (1 + 0.2 * torch.randn(C, device=dev, generator=g)).to(dtype)
+    b = (0.3 * torch.randn(C, device=dev, generator=g)).to(dtype)
+    y = ops.layer_norm(x, w, b, 1e-5)
+    ref = torch.nn.functional.layer_norm(x.float(), (C,), w.float(), b.float(), 1e-5)
+    assert y.dtype == dtype and y.shape == x.shape
+    assert float((y.float() - ref).abs().max()) <= tol * max(1.0, float(ref.abs().max()))
+    lib = torch.nn.functional.layer_norm(x, (C,), w, b, 1e-5)
+    assert float((y.float() - lib.float()).abs().max()) <= tol * max(1.0, float(ref.abs().max()))
