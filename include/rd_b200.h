@@ -213,17 +213,6 @@ int rd_groupnorm_nhwc(const void* x, void* y, const void* gamma, const void* bet
                       int N, int HW, int C, int G, float eps, int act, rd_dtype dtype,
                       void* workspace, int64_t workspace_bytes, void* stream);
 
-/* The same GroupNorm with the statistics taken by the pass that PRODUCED x ("GroupNorm statistics fused
- * into the producing pass"): rd_bias_residual_stats_nhwc writes y = x + bias[c] + vec[n, c] + residual like
- * rd_bias_residual_nhwc and leaves the per-(sample, chunk, group) sums of y in `stats` (rd_groupnorm_workspace_bytes(N, G) bytes,
- * same layout the two-kernel entry point uses internally); rd_groupnorm_apply_nhwc then normalises that tensor from `stats` in
- * one read + one write instead of two reads + one write.  Used for the norm1 of every resnet whose input comes out of the
- * previous resnet's skip-connection pass or out of an upsampler / conv_in bias pass (resnet.py:338-339). */
-int rd_bias_residual_stats_nhwc(const void* x, const void* bias, const void* vec, const void* residual, void* y,
-                                int N, int HW, int C, int G, rd_dtype dtype, void* stats, int64_t stats_bytes, void* stream);
-int rd_groupnorm_apply_nhwc(const void* x, void* y, const void* gamma, const void* beta, int N, int HW, int C, int G, float eps,
-                            int act, rd_dtype dtype, const void* stats, int64_t stats_bytes, void* stream);
-
 /* y = x + bias[c] + vec[n, c] + residual in one vectorised pass over [N, HW, C] (any of bias / vec / residual may be
  * NULL; y may alias x): conv bias, time-embedding add and skip connection (resnet.py:341-376) without separate
  * element-wise launches.  Arithmetic in fp32, one rounding. */

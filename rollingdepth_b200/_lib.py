@@ -92,8 +92,6 @@ SIGNATURES = {
     "rd_groupnorm_workspace_bytes": (_I64, [_I, _I]),
     "rd_groupnorm_nhwc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _I, _P, _I64, _P]),
     "rd_bias_residual_nhwc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
-    "rd_bias_residual_stats_nhwc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _I64, _P]),
-    "rd_groupnorm_apply_nhwc": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _I, _P, _I64, _P]),
     "rd_upsample_nearest_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
     "rd_geglu": (_I, [_P, _P, _I64, _I, _I, _P]),
     "rd_softmax_rows": (_I, [_P, _P, _I64, _I, _F, _I, _P]),

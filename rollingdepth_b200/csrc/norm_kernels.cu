@@ -25,9 +25,6 @@ struct GnParams {
     const void* gamma;
     const void* beta;
     const void* pre;      // optional [N][C] vector added to x before the statistics (conv bias + time embedding)
-    const void* res;      // fused producer (gn_stats_kernel<T, true>): y = x + res + bias[c] + vec[n][c], statistics of y
-    const void* bias;
-    const void* vec;
     double* partial;      // [N][chunks][G][2]  (sum x, sum x^2)
     int N, HW, C, G, cpg;  // cpg = channels per group
     int Cs;                // channels per CTA slice (blockIdx.z selects the slice); Cs % cpg == 0
@@ -52,10 +49,7 @@ __device__ __forceinline__ void gn_unpack(const uint4& u, float* f) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// ADD = true: the kernel is the PRODUCER of the tensor whose statistics it takes -- y = T(x + res + bias[c] + vec[n][c])
-// (the conv-bias / time-embedding / skip-connection pass of rd_bias_residual_nhwc) is written and its per-(sample, chunk,
-// group) sums are accumulated in the same pass, so the GroupNorm that consumes y skips its own statistics pass.
-template <typename T, bool ADD = false>
+template <typename T>
 __global__ void __launch_bounds__(kGnMaxThreads, 2) gn_stats_kernel(const GnParams p) {
     constexpr int VN = GnVec<T>::N;
     extern __shared__ __align__(16) double sh_d[];                  // [2][Cs] channel sums (double), then float [2][R][Cs] + [Cs]
@@ -73,79 +67,6 @@ __global__ void __launch_bounds__(kGnMaxThreads, 2) gn_stats_kernel(const GnPara
     const int row1 = min(p.HW, row0 + p.rows_per_chunk);
 
     float shift[VN], s1[VN], s2[VN], pre[VN];
-    if constexpr (ADD) {
-        // fused producer.  `pre` holds the per-(sample, channel) addend; the shift is the result at the chunk's first row
-        // (read before anything is written: y may alias x)
-        const T* rs = p.res ? reinterpret_cast<const T*>(p.res) + (size_t)n * p.HW * p.C + c_off : nullptr;
-        T* ys = reinterpret_cast<T*>(p.y) + (size_t)n * p.HW * p.C + c_off;
-        auto result = [&](const uint4& xin, const uint4& rin, float (&o)[VN]) {
-            gn_unpack<T>(xin, o);
-            if (rs) {
-                float g[VN];
-                gn_unpack<T>(rin, g);
-#pragma unroll
-                for (int i = 0; i < VN; ++i) o[i] += g[i];
-            }
-#pragma unroll
-            for (int i = 0; i < VN; ++i) o[i] = Cvt<T>::round(o[i] + pre[i]);
-        };
-        if (active) {
-#pragma unroll
-            for (int i = 0; i < VN; ++i) { pre[i] = 0.f; s1[i] = 0.f; s2[i] = 0.f; }
-            if (p.bias) {
-                float t[VN];
-                gn_unpack<T>(*reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.bias) + c_off + cv * VN), t);
-#pragma unroll
-                for (int i = 0; i < VN; ++i) pre[i] += t[i];
-            }
-            if (p.vec) {
-                float t[VN];
-                gn_unpack<T>(*reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.vec) + (size_t)n * p.C + c_off + cv * VN), t);
-#pragma unroll
-                for (int i = 0; i < VN; ++i) pre[i] += t[i];
-            }
-            const size_t o0 = (size_t)row0 * p.C + cv * VN;
-            const uint4 x0 = ldg_stream16(xs + o0);
-            result(x0, rs ? ldg_stream16(rs + o0) : x0, shift);
-        }
-        __syncthreads();                    // every thread has its shift before the first store (in-place operation)
-        if (active) {
-            auto emit = [&](const uint4& xin, const uint4& rin, size_t off) {
-                float o[VN];
-                result(xin, rin, o);
-                alignas(16) T ob[VN];
-#pragma unroll
-                for (int i = 0; i < VN; ++i) {
-                    ob[i] = Cvt<T>::from_f(o[i]);
-                    const float d = o[i] - shift[i];
-                    s1[i] += d;
-                    s2[i] = fmaf(d, d, s2[i]);
-                }
-                *reinterpret_cast<uint4*>(ys + off) = *reinterpret_cast<const uint4*>(ob);
-            };
-            int row = row0 + r;
-            for (; row + 3 * p.R < row1; row += 4 * p.R) {          // up to eight 16-byte loads in flight per thread
-                size_t off[4];
-                uint4 xin[4], rin[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    off[u] = (size_t)(row + u * p.R) * p.C + cv * VN;
-                    xin[u] = ldg_stream16(xs + off[u]);
-                }
-                if (rs) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) rin[u] = ldg_stream16(rs + off[u]);
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) emit(xin[u], rin[u], off[u]);
-            }
-            for (; row < row1; row += p.R) {
-                const size_t off = (size_t)row * p.C + cv * VN;
-                const uint4 xin = ldg_stream16(xs + off);
-                emit(xin, rs ? ldg_stream16(rs + off) : xin, off);
-            }
-        }
-    } else
     if (active) {
 #pragma unroll
         for (int i = 0; i < VN; ++i) pre[i] = 0.f;
@@ -182,8 +103,6 @@ __global__ void __launch_bounds__(kGnMaxThreads, 2) gn_stats_kernel(const GnPara
                 s2[i] = fmaf(da, da, s2[i]);
             }
         }
-    }
-    if (active) {
         // park the per-thread shifted sums; the row-threads of a channel are combined below in the order r = 0..R-1
         float* d1 = st1 + (size_t)r * p.Cs + cv * VN;
         float* d2 = st2 + (size_t)r * p.Cs + cv * VN;
@@ -565,59 +484,6 @@ static int gn_plan(GnParams& p, int es) {
     return 0;
 }
 
-// shared by the three GroupNorm entry points: argument checks, plan, kernel attributes
-static int gn_setup(GnParams& p, const void* x, void* y, int N, int HW, int C, int G, rd_dtype dtype, int64_t workspace_bytes) {
-    RD_CHECK_ARG(x && y, "NULL pointer");
-    RD_CHECK_ARG(N >= 1 && HW >= 1 && C >= 1 && G >= 1 && G <= 64 && C % G == 0, "bad shape N=%d HW=%d C=%d G=%d", N, HW, C, G);
-    RD_CHECK_ARG(N <= 65535, "N must be <= 65535");
-    RD_CHECK_ARG(dtype == RD_F32 || dtype == RD_F16 || dtype == RD_BF16, "bad dtype");
-    const int es = dtype == RD_F32 ? 4 : 2;
-    if (C % (16 / es) != 0) { set_error("C=%d is not a multiple of the 16-byte vector width", C); return RD_ERR_UNSUPPORTED; }
-    RD_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "x / y must be 16-byte aligned");
-    p.x = x; p.y = y;
-    p.N = N; p.HW = HW; p.C = C; p.G = G; p.cpg = C / G;
-    if (gn_plan(p, es) != 0) { set_error("no channel slicing found for C=%d G=%d", C, G); return RD_ERR_UNSUPPORTED; }
-    if (workspace_bytes < (int64_t)N * p.chunks * G * 2 * (int64_t)sizeof(double)) {
-        set_error("group-norm workspace too small");
-        return RD_ERR_WORKSPACE;
-    }
-    // up to 16 B * Cs + 8 B * R * Cs = 96 KB for the widest slice: opt in above the 48 KB default (per device)
-    static PerDeviceOnce configured;
-    if (configured.needed()) {
-        RD_CUDA(cudaFuncSetAttribute(gn_stats_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        RD_CUDA(cudaFuncSetAttribute(gn_stats_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        RD_CUDA(cudaFuncSetAttribute(gn_stats_kernel<__nv_bfloat16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        RD_CUDA(cudaFuncSetAttribute(gn_stats_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        RD_CUDA(cudaFuncSetAttribute(gn_stats_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        RD_CUDA(cudaFuncSetAttribute(gn_stats_kernel<__nv_bfloat16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        configured.done();
-    }
-    return RD_OK;
-}
-
-template <bool ADD>
-static void gn_launch_stats(const GnParams& p, rd_dtype dtype, cudaStream_t st) {
-    const int threads = p.CV * p.R;
-    dim3 grid(p.chunks, p.N, p.C / p.Cs);
-    const size_t sm = 2 * (size_t)p.Cs * sizeof(double) + (2 * (size_t)p.R + 1) * p.Cs * sizeof(float);
-    switch (dtype) {
-        case RD_F32: gn_stats_kernel<float, ADD><<<grid, threads, sm, st>>>(p); break;
-        case RD_F16: gn_stats_kernel<__half, ADD><<<grid, threads, sm, st>>>(p); break;
-        default:     gn_stats_kernel<__nv_bfloat16, ADD><<<grid, threads, sm, st>>>(p); break;
-    }
-}
-
-static void gn_launch_apply(const GnParams& p, rd_dtype dtype, cudaStream_t st) {
-    const int threads = p.CV * p.R;
-    dim3 grid(p.chunks, p.N, p.C / p.Cs);
-    const size_t sm = 2 * (size_t)p.Cs * sizeof(float);
-    switch (dtype) {
-        case RD_F32: gn_apply_kernel<float><<<grid, threads, sm, st>>>(p); break;
-        case RD_F16: gn_apply_kernel<__half><<<grid, threads, sm, st>>>(p); break;
-        default:     gn_apply_kernel<__nv_bfloat16><<<grid, threads, sm, st>>>(p); break;
-    }
-}
-
 }  // namespace rd
 
 using namespace rd;
@@ -631,48 +497,55 @@ int64_t rd_groupnorm_workspace_bytes(int N, int G) {
 int rd_groupnorm_nhwc(const void* x, void* y, const void* gamma, const void* beta, const void* pre_add, int N, int HW,
                       int C, int G, float eps, int act, rd_dtype dtype, void* workspace, int64_t workspace_bytes,
                       void* stream) {
-    RD_CHECK_ARG(workspace != nullptr, "NULL workspace");
+    RD_CHECK_ARG(x && y && workspace, "NULL pointer");
+    RD_CHECK_ARG(N >= 1 && HW >= 1 && C >= 1 && G >= 1 && G <= 64 && C % G == 0, "bad shape N=%d HW=%d C=%d G=%d", N, HW, C, G);
+    RD_CHECK_ARG(N <= 65535, "N must be <= 65535");
     RD_CHECK_ARG(act == 0 || act == 1, "act must be 0 (none) or 1 (SiLU)");
-    RD_CHECK_ARG(((uintptr_t)pre_add & 15) == 0, "pre_add must be 16-byte aligned");
+    RD_CHECK_ARG(dtype == RD_F32 || dtype == RD_F16 || dtype == RD_BF16, "bad dtype");
+    const int es = dtype == RD_F32 ? 4 : 2;
+    if (C % (16 / es) != 0) { set_error("C=%d is not a multiple of the 16-byte vector width", C); return RD_ERR_UNSUPPORTED; }
+    RD_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 && ((uintptr_t)pre_add & 15) == 0,
+                 "x / y / pre_add must be 16-byte aligned");
     GnParams p{};
-    if (int e = gn_setup(p, x, y, N, HW, C, G, dtype, workspace_bytes)) return e;
-    p.gamma = gamma; p.beta = beta; p.pre = pre_add;
+    p.x = x; p.y = y; p.gamma = gamma; p.beta = beta; p.pre = pre_add;
     p.partial = reinterpret_cast<double*>(workspace);
-    p.eps = eps; p.act = act;
-    // (a cp.async staging ring holding eight 16-byte loads per thread in shared memory instead of four in registers was
-    //  measured 3-6 % SLOWER on the three decoder sizes -- profiles/r2_gn_variants.txt -- and is not kept)
+    p.N = N; p.HW = HW; p.C = C; p.G = G; p.cpg = C / G; p.eps = eps; p.act = act;
+    if (gn_plan(p, es) != 0) { set_error("no channel slicing found for C=%d G=%d", C, G); return RD_ERR_UNSUPPORTED; }
+    if (workspace_bytes < (int64_t)N * p.chunks * G * 2 * (int64_t)sizeof(double)) {
+        set_error("group-norm workspace too small");
+        return RD_ERR_WORKSPACE;
+    }
     cudaStream_t st = (cudaStream_t)stream;
-    gn_launch_stats<false>(p, dtype, st);
-    gn_launch_apply(p, dtype, st);
+    const int threads = p.CV * p.R;
+    dim3 grid(p.chunks, N, C / p.Cs);
+    // (a cp.async staging ring holding eight 16-byte loads per thread in shared memory instead of four in registers was
+    //  measured 3-6 % SLOWER on the three decoder sizes -- tools/probes, profiles/r2_gn_variants.txt -- and is not kept)
+    const size_t sm_stats = 2 * (size_t)p.Cs * sizeof(double) + (2 * (size_t)p.R + 1) * p.Cs * sizeof(float);
+    const size_t sm_apply = 2 * (size_t)p.Cs * sizeof(float);
+    {   // up to 16 B * Cs + 8 B * R * Cs = 96 KB for the widest slice: opt in above the 48 KB default (per device)
+        static PerDeviceOnce configured;
+        if (configured.needed()) {
+            RD_CUDA(cudaFuncSetAttribute(gn_stats_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            RD_CUDA(cudaFuncSetAttribute(gn_stats_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            RD_CUDA(cudaFuncSetAttribute(gn_stats_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            configured.done();
+        }
+    }
+    switch (dtype) {
+        case RD_F32:
+            gn_stats_kernel<float><<<grid, threads, sm_stats, st>>>(p);
+            gn_apply_kernel<float><<<grid, threads, sm_apply, st>>>(p);
+            break;
+        case RD_F16:
+            gn_stats_kernel<__half><<<grid, threads, sm_stats, st>>>(p);
+            gn_apply_kernel<__half><<<grid, threads, sm_apply, st>>>(p);
+            break;
+        default:
+            gn_stats_kernel<__nv_bfloat16><<<grid, threads, sm_stats, st>>>(p);
+            gn_apply_kernel<__nv_bfloat16><<<grid, threads, sm_apply, st>>>(p);
+            break;
+    }
     RD_LAUNCH_CHECK("gn kernels");
-    return RD_OK;
-}
-
-int rd_groupnorm_apply_nhwc(const void* x, void* y, const void* gamma, const void* beta, int N, int HW, int C, int G, float eps,
-                            int act, rd_dtype dtype, const void* stats, int64_t stats_bytes, void* stream) {
-    RD_CHECK_ARG(stats != nullptr, "NULL statistics");
-    RD_CHECK_ARG(act == 0 || act == 1, "act must be 0 (none) or 1 (SiLU)");
-    GnParams p{};
-    if (int e = gn_setup(p, x, y, N, HW, C, G, dtype, stats_bytes)) return e;
-    p.gamma = gamma; p.beta = beta; p.pre = nullptr;
-    p.partial = reinterpret_cast<double*>(const_cast<void*>(stats));
-    p.eps = eps; p.act = act;
-    gn_launch_apply(p, dtype, (cudaStream_t)stream);
-    RD_LAUNCH_CHECK("gn_apply_kernel");
-    return RD_OK;
-}
-
-int rd_bias_residual_stats_nhwc(const void* x, const void* bias, const void* vec, const void* residual, void* y, int N, int HW,
-                                int C, int G, rd_dtype dtype, void* stats, int64_t stats_bytes, void* stream) {
-    RD_CHECK_ARG(stats != nullptr, "NULL statistics buffer");
-    RD_CHECK_ARG((((uintptr_t)bias | (uintptr_t)vec | (uintptr_t)residual) & 15) == 0, "pointers must be 16-byte aligned");
-    GnParams p{};
-    if (int e = gn_setup(p, x, y, N, HW, C, G, dtype, stats_bytes)) return e;
-    if (p.C != p.Cs) { set_error("C=%d: the fused statistics need one channel slice", C); return RD_ERR_UNSUPPORTED; }
-    p.res = residual; p.bias = bias; p.vec = vec;
-    p.partial = reinterpret_cast<double*>(stats);
-    gn_launch_stats<true>(p, dtype, (cudaStream_t)stream);
-    RD_LAUNCH_CHECK("gn_stats_kernel (fused producer)");
     return RD_OK;
 }
 

@@ -104,49 +104,29 @@ def _opt(t: Optional[torch.Tensor], dtype) -> Optional[torch.Tensor]:
     return None if t is None else t.to(dtype).contiguous()
 
 
-_GN_STATS_ATTR = "_rd_gn_stats"      # (statistics workspace, num_groups) left on a tensor by the pass that produced it
-
-
 def group_norm_nhwc(x: torch.Tensor, num_groups: int, weight: Optional[torch.Tensor], bias: Optional[torch.Tensor],
                     eps: float, silu: bool, pre_add: Optional[torch.Tensor] = None) -> torch.Tensor:
     """act(GroupNorm(x + pre_add[n, c])) on a channels-last activation ([N, C, H, W] in torch.channels_last
-    memory format or [N, L, C] contiguous); same shape / memory format out.  If `x` still carries the statistics its
-    producer took (`bias_residual_nhwc(..., stats_groups=G)`), only the normalising pass runs."""
+    memory format or [N, L, C] contiguous); same shape / memory format out."""
     L.require_cuda(x)
     N, HW, Cc = _nhwc_dims(x)
     y = torch.empty_like(x)          # preserve_format keeps channels_last
     lib = L.lib()
-    g, b, pre = _opt(weight, x.dtype), _opt(bias, x.dtype), _opt(pre_add, x.dtype)
-    P = lambda t: L.ptr(t) if t is not None else None
-    carried = getattr(x, _GN_STATS_ATTR, None)
-    if carried is not None and pre is None and carried[1] == int(num_groups):
-        ws = carried[0]
-        L.call("rd_groupnorm_apply_nhwc", x.device, L.ptr(x), L.ptr(y), P(g), P(b), N, HW, Cc, int(num_groups), float(eps),
-               1 if silu else 0, L.dtype_code(x.dtype), L.ptr(ws), ws.numel(), L.stream_ptr(x.device))
-        L.count_launches(1)
-        return y
     ws_bytes = lib.rd_groupnorm_workspace_bytes(N, num_groups)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    g, b, pre = _opt(weight, x.dtype), _opt(bias, x.dtype), _opt(pre_add, x.dtype)
     if pre is not None and tuple(pre.shape) != (N, Cc):
         raise L.RdError(f"pre_add must be [{N}, {Cc}], got {tuple(pre.shape)}")
+    P = lambda t: L.ptr(t) if t is not None else None
     L.call("rd_groupnorm_nhwc", x.device, L.ptr(x), L.ptr(y), P(g), P(b), P(pre), N, HW, Cc, int(num_groups), float(eps),
            1 if silu else 0, L.dtype_code(x.dtype), L.ptr(ws), ws_bytes, L.stream_ptr(x.device))
     L.count_launches(2)
     return y
 
 
-def _stats_fusable(Cc: int, num_groups: int, es: int) -> bool:
-    """One channel slice per CTA row (C / vector width <= 512 vectors) and whole groups."""
-    return num_groups >= 1 and Cc % num_groups == 0 and Cc % (16 // es) == 0 and Cc // (16 // es) <= 512 and num_groups <= 64
-
-
 def bias_residual_nhwc(x: torch.Tensor, bias: Optional[torch.Tensor] = None, vec: Optional[torch.Tensor] = None,
-                       residual: Optional[torch.Tensor] = None, inplace: bool = True,
-                       stats_groups: Optional[int] = None) -> torch.Tensor:
-    """x + bias[c] + vec[n, c] + residual in one pass (channels-last).  `stats_groups = G`: the same pass also takes the
-    GroupNorm statistics of the result for G groups and leaves them on the returned tensor, so that a following
-    `group_norm_nhwc(result, G, ...)` skips its statistics pass (the attribute dies with the tensor object; any op that
-    makes a new tensor simply falls back to the two-pass GroupNorm)."""
+                       residual: Optional[torch.Tensor] = None, inplace: bool = True) -> torch.Tensor:
+    """x + bias[c] + vec[n, c] + residual in one pass (channels-last)."""
     L.require_cuda(x)
     N, HW, Cc = _nhwc_dims(x)
     if residual is not None:
@@ -156,16 +136,6 @@ def bias_residual_nhwc(x: torch.Tensor, bias: Optional[torch.Tensor] = None, vec
     y = x if inplace else torch.empty_like(x)
     b, v = _opt(bias, x.dtype), _opt(vec, x.dtype)
     P = lambda t: L.ptr(t) if t is not None else None
-    if stats_groups is not None and _stats_fusable(Cc, int(stats_groups), x.element_size()):
-        G = int(stats_groups)
-        ws = torch.empty(L.lib().rd_groupnorm_workspace_bytes(N, G), dtype=torch.uint8, device=x.device)
-        L.call("rd_bias_residual_stats_nhwc", x.device, L.ptr(x), P(b), P(v), P(residual), L.ptr(y), N, HW, Cc, G,
-               L.dtype_code(x.dtype), L.ptr(ws), ws.numel(), L.stream_ptr(x.device))
-        L.count_launches(1)
-        setattr(y, _GN_STATS_ATTR, (ws, G))
-        return y
-    if hasattr(y, _GN_STATS_ATTR):
-        delattr(y, _GN_STATS_ATTR)          # the tensor is being overwritten in place: stale statistics must not survive
     L.call("rd_bias_residual_nhwc", x.device, L.ptr(x), P(b), P(v), P(residual), L.ptr(y), N, HW, Cc,
            L.dtype_code(x.dtype), L.stream_ptr(x.device))
     L.count_launches(1)

@@ -81,14 +81,13 @@ class BiasConv2d(nn.Conv2d):
     (rd_bias_residual_nhwc) instead of torch's broadcast add, which is not vectorised for NHWC tensors."""
 
     fused = False
-    emit_gn_groups = None       # G: the bias pass also takes GroupNorm statistics for the resnet norm1 that consumes its output
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if self.fused and x.is_cuda and self.bias is not None and self.out_channels % (16 // x.element_size()) == 0:
             y = F.conv2d(x, self.weight, None, self.stride, self.padding, self.dilation, self.groups)
             if _is_cl(y):
                 from .. import ops
-                return ops.bias_residual_nhwc(y, bias=self.bias, stats_groups=self.emit_gn_groups)
+                return ops.bias_residual_nhwc(y, bias=self.bias)
             return y + self.bias.view(1, -1, 1, 1)
         return super().forward(x)
 
@@ -384,7 +383,6 @@ class ResnetBlock2D(nn.Module):
         self.conv_shortcut = BiasConv2d(in_channels, out_channels, 1) if in_channels != out_channels else None
         self.output_scale_factor = output_scale_factor
         self.fused = False
-        self.emit_stats = True      # cleared for resnets whose output does not go into a GroupNorm (e.g. before an upsampler)
 
     def _forward_fused(self, x, temb):
         """Same arithmetic with the element-wise passes folded away: conv1's bias and the projected time
@@ -403,9 +401,7 @@ class ResnetBlock2D(nn.Module):
         if self.conv_shortcut is not None:
             x = F.conv2d(x, self.conv_shortcut.weight, None)
             bias = bias + self.conv_shortcut.bias
-        # the skip-connection pass also takes the GroupNorm statistics of its result: the next resnet's norm1 (same group
-        # count throughout these models) then needs one pass instead of two
-        out = ops.bias_residual_nhwc(h, bias=bias, residual=x, stats_groups=self.norm1.num_groups if self.emit_stats else None)
+        out = ops.bias_residual_nhwc(h, bias=bias, residual=x)
         return out if self.output_scale_factor == 1.0 else out / self.output_scale_factor
 
     def forward(self, x, temb=None):

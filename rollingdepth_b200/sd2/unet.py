@@ -38,10 +38,6 @@ class _DownBlock(nn.Module):
         else:
             self.attentions = None
         self.downsamplers = nn.ModuleList([Downsample2D(cout, padding=1)]) if add_down else None
-        if add_down:        # the next block's first norm1 reads the downsampler's output: its bias pass takes the statistics
-            self.downsamplers[0].conv.emit_gn_groups = groups
-            if self.attentions is None:
-                self.resnets[-1].emit_stats = False
 
     def forward(self, x, temb, ctx, num_view):
         outs = ()
@@ -61,7 +57,6 @@ class _MidBlock(nn.Module):
         super().__init__()
         self.resnets = nn.ModuleList([ResnetBlock2D(c, c, temb, groups), ResnetBlock2D(c, c, temb, groups)])
         self.attentions = nn.ModuleList([Transformer2DModel(heads, c // heads, c, 1, cross, groups, linear)])
-        self.resnets[1].emit_stats = False          # its output is concatenated with a skip tensor in the first up block
 
     def forward(self, x, temb, ctx, num_view):
         x = self.resnets[0](x, temb)
@@ -84,8 +79,6 @@ class _UpBlock(nn.Module):
                 [Transformer2DModel(heads, cout // heads, cout, 1, cross, groups, linear) for _ in range(layers)])
         else:
             self.attentions = None
-            for r in self.resnets:                  # outputs go into a concatenation / the upsampler, not into a GroupNorm
-                r.emit_stats = False
         self.upsamplers = nn.ModuleList([Upsample2D(cout)]) if add_up else None
 
     def forward(self, x, skips: Tuple[torch.Tensor, ...], temb, ctx, num_view, upsample_size=None):
@@ -137,7 +130,6 @@ class UNet2DConditionModel(nn.Module):
         heads = (heads,) * nb if isinstance(heads, int) else tuple(heads)
         temb = block_out_channels[0] * 4
         self.conv_in = BiasConv2d(in_channels, block_out_channels[0], 3, padding=1)
-        self.conv_in.emit_gn_groups = norm_num_groups
         self.time_embedding = TimestepEmbedding(block_out_channels[0], temb)
 
         self.down_blocks = nn.ModuleList()

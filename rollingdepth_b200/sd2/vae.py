@@ -28,7 +28,6 @@ class _VaeMid(nn.Module):
             Attention(c, None, heads=c // attention_head_dim, dim_head=attention_head_dim, bias=True,
                       norm_num_groups=groups, eps=1e-6, residual_connection=True, rescale_output_factor=1.0)])
         self.resnets = nn.ModuleList([ResnetBlock2D(c, c, None, groups, eps=1e-6), ResnetBlock2D(c, c, None, groups, eps=1e-6)])
-        self.resnets[0].emit_stats = False          # its output goes into the attention (a reshaped view), not a norm1
 
     def forward(self, x):
         x = self.resnets[0](x)
@@ -41,9 +40,6 @@ class _EncBlock(nn.Module):
         super().__init__()
         self.resnets = nn.ModuleList([ResnetBlock2D(cin if i == 0 else cout, cout, None, groups, eps=1e-6) for i in range(layers)])
         self.downsamplers = nn.ModuleList([Downsample2D(cout, padding=0)]) if add_down else None
-        if add_down:        # GroupNorm statistics travel with the tensor that the next norm1 reads: the downsampler's output
-            self.resnets[-1].emit_stats = False
-            self.downsamplers[0].conv.emit_gn_groups = groups
 
     def forward(self, x):
         for r in self.resnets:
@@ -58,9 +54,6 @@ class _DecBlock(nn.Module):
         super().__init__()
         self.resnets = nn.ModuleList([ResnetBlock2D(cin if i == 0 else cout, cout, None, groups, eps=1e-6) for i in range(layers)])
         self.upsamplers = nn.ModuleList([Upsample2D(cout)]) if add_up else None
-        if add_up:
-            self.resnets[-1].emit_stats = False
-            self.upsamplers[0].conv.emit_gn_groups = groups
 
     def forward(self, x):
         for r in self.resnets:
@@ -74,7 +67,6 @@ class Encoder(nn.Module):
     def __init__(self, in_channels, out_channels, block_out_channels: Sequence[int], layers_per_block, groups, double_z=True):
         super().__init__()
         self.conv_in = BiasConv2d(in_channels, block_out_channels[0], 3, padding=1)
-        self.conv_in.emit_gn_groups = groups
         self.down_blocks = nn.ModuleList()
         cout = block_out_channels[0]
         for i, c in enumerate(block_out_channels):
@@ -98,7 +90,6 @@ class Decoder(nn.Module):
         super().__init__()
         rev = list(reversed(block_out_channels))
         self.conv_in = BiasConv2d(in_channels, rev[0], 3, padding=1)
-        self.conv_in.emit_gn_groups = groups
         self.mid_block = _VaeMid(rev[0], groups, rev[0])
         self.up_blocks = nn.ModuleList()
         cout = rev[0]

@@ -637,41 +637,3 @@ def test_layernorm_matches_torch_fp32(M, C, dtype, tol):
     assert float((y.float() - ref).abs().max()) <= tol * max(1.0, float(ref.abs().max()))
     lib = torch.nn.functional.layer_norm(x, (C,), w, b, 1e-5)
     assert float((y.float() - lib.float()).abs().max()) <= tol * max(1.0, float(ref.abs().max()))
-
-
-# =============================================================================== GroupNorm statistics taken by the producer
-@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
-@pytest.mark.parametrize("shape", [(3, 128, 37, 53), (2, 320, 27, 48), (2, 512, 54, 96), (1, 1280, 14, 24)])
-@pytest.mark.parametrize("inplace", [False, True])
-def test_bias_residual_with_groupnorm_statistics(shape, dtype, inplace):
-    """rd_bias_residual_stats_nhwc + rd_groupnorm_apply_nhwc: the producing pass writes exactly what
-    rd_bias_residual_nhwc writes, and the GroupNorm fed from its statistics equals the two-pass GroupNorm of that tensor
-    (and the fp32 torch reference) -- including in-place operation, where the input is overwritten while it is read."""
-    from rollingdepth_b200 import ops
-    dev = _dev()
-    N, C, H, W = shape
-    g = torch.Generator().manual_seed(C + W)
-    mk = lambda *sz: (torch.randn(*sz, generator=g) * 1.5).to(dtype).to(dev)
-    x = (mk(N, C, H, W) + mk(1, C, 1, 1) * 2).contiguous(memory_format=torch.channels_last)
-    r = mk(N, C, H, W).contiguous(memory_format=torch.channels_last)
-    b, v = mk(C), mk(N, C)
-    wt, bs = (1 + 0.2 * mk(C)), 0.3 * mk(C)
-    plain = ops.bias_residual_nhwc(x, bias=b, vec=v, residual=r, inplace=False)
-    xin = x.clone(memory_format=torch.preserve_format) if inplace else x
-    y = ops.bias_residual_nhwc(xin, bias=b, vec=v, residual=r, inplace=inplace, stats_groups=32)
-    assert hasattr(y, ops._GN_STATS_ATTR) and (y is xin) == inplace
-    assert torch.equal(y, plain)
-    two_pass = ops.group_norm_nhwc(plain, 32, wt, bs, 1e-6, True)
-    one_pass = ops.group_norm_nhwc(y, 32, wt, bs, 1e-6, True)
-    ref = torch.nn.functional.silu(torch.nn.functional.group_norm(plain.float(), 32, wt.float(), bs.float(), 1e-6))
-    tol = {torch.float16: 4e-3, torch.bfloat16: 3e-2, torch.float32: 2e-5}[dtype]
-    assert float((one_pass.float() - ref).abs().max()) <= tol * max(1.0, float(ref.abs().max()))
-    assert float((one_pass.float() - two_pass.float()).abs().max()) <= tol * max(1.0, float(ref.abs().max()))
-    # a different group count, a pre-add, or a new tensor object must not pick the statistics up
-    again = ops.group_norm_nhwc(y, 16, wt, bs, 1e-6, False)
-    assert float((again.float() - torch.nn.functional.group_norm(plain.float(), 16, wt.float(), bs.float(), 1e-6)).abs().max()) \
-        <= tol * max(1.0, float(ref.abs().max()))
-    assert not hasattr(y * 1, ops._GN_STATS_ATTR)
-    # overwriting the tensor in place without statistics drops the stale ones
-    z = ops.bias_residual_nhwc(y, bias=b, inplace=True)
-    assert z is y and not hasattr(z, ops._GN_STATS_ATTR)
