@@ -395,7 +395,8 @@ def run_ours(args):
 
     def step(frames):
         return pipe.forward(input_frames=frames, dilations=list(dil), cap_dilation=cap, snippet_lengths=[3],
-                            init_infer_steps=[1], strides=[1], coalign_kwargs=None, refine_step=refine,
+                            init_infer_steps=[1], strides=[1],
+                            coalign_kwargs=dict(num_iterations=args.coalign_its) if args.coalign_its else None, refine_step=refine,
                             refine_snippet_len=3, refine_start_dilation=6,
                             generator=torch.Generator(device=dev).manual_seed(0), verbose=False,
                             max_vae_bs=args.max_vae_bs, unload_snippet=False)
@@ -537,6 +538,8 @@ if __name__ == "__main__":
                     help="time the reference's GPU path as context (N = 1 only): bounded sample (default) or the whole clip")
     ap.add_argument("--cpu-full", action="store_true", help="--impl reference: the whole pass on CPU, no extrapolation")
     ap.add_argument("--stage-times", action="store_true", help="add per-stage device times of the last timed step (rank 0)")
+    ap.add_argument("--coalign-its", type=int, default=0,
+                    help="profiling only: fewer co-alignment iterations than the reference's 2000 (ncu launch list); NOT a bench configuration")
     ap.add_argument("--frames", type=int, default=0,
                     help="profiling only: shorter clip than the preset (the ncu launch list); NOT a bench configuration")
     a = ap.parse_args()

@@ -96,6 +96,22 @@ def bench_attn(args):
                 print(json.dumps(rec), flush=True)
 
 
+def bench_attn_fp32(args):
+    """The fp32 attention path (`paper` preset / cfg1: a plain FFMA kernel, <= 1e-4) against torch SDPA in fp32."""
+    from rollingdepth_b200 import ops
+    dev = torch.device("cuda:0")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    for name, B, S, H in [("cfg1 L0 (256x256 n=3)", 1, 3072, 5), ("paper L0 (768x432 n=3)", 1, 15552, 5), ("paper L1", 1, 3888, 10)]:
+        q, k, v = [torch.randn(B, S, H * 64, device=dev).view(B, S, H, 64) for _ in range(3)]
+        out = torch.empty_like(q)
+        flops = 4.0 * B * H * S * S * 64
+        med, _ = time_cuda(lambda: ops.xattn_fwd(q, k, v, out=out), iters=5)
+        qt, kt, vt = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
+        m2, _ = time_cuda(lambda: torch.nn.functional.scaled_dot_product_attention(qt, kt, vt), iters=5)
+        print(json.dumps(dict(bench="xattn_fp32", case=name, S=S, H=H, ms=med, tflops=flops / med / 1e9, torch_sdpa_fp32_ms=m2,
+                              torch_sdpa_fp32_tflops=flops / m2 / 1e9)), flush=True)
+
+
 def bench_align(args):
     from rollingdepth_b200.depth_aligner import DepthAligner
     from oracle.gen_golden import synth_snippets  # generator only (inputs), not a compute path
@@ -180,7 +196,7 @@ def bench_gn(args):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["attn", "align", "gn"])
+    ap.add_argument("what", choices=["attn", "attn_fp32", "align", "gn"])
     ap.add_argument("--full", action="store_true")
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--iters", type=int, default=200)
@@ -188,4 +204,4 @@ if __name__ == "__main__":
     ap.add_argument("--only", default="")
     ap.add_argument("--no-sdpa", action="store_true", help="skip the torch SDPA comparators")
     a = ap.parse_args()
-    {"attn": bench_attn, "align": bench_align, "gn": bench_gn}[a.what](a)
+    {"attn": bench_attn, "attn_fp32": bench_attn_fp32, "align": bench_align, "gn": bench_gn}[a.what](a)
