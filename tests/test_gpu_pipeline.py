@@ -209,3 +209,30 @@ def test_output_modes_agree_and_results_are_fresh_by_default(golden_dir):
     assert torch.equal(c.depth_pred, a.depth_pred) and torch.equal(c.depth_coaligned, a.depth_coaligned)
     for x, y in zip(c.snippet_ls, a.snippet_ls):
         assert torch.equal(x, y)
+
+
+def test_unload_snippet_and_uncovered_refinement(golden_dir):
+    """`unload_snippet=True` (rollingdepth_pipeline.py:448-449: decoded snippets parked on the host, moved back by the
+    aligner) gives the same result as keeping them on the device; a refinement schedule whose windows leave frames uncovered
+    (`cap_dilation=False` with a start dilation larger than the window count) raises like the reference's
+    `assert torch.all(count_depth_latent_new > 0)` (:628) instead of dividing by zero."""
+    from rollingdepth_b200.pipeline import RollingDepthPipeline
+    from rollingdepth_b200.scheduler import DDIMSchedule
+    dev = _dev()
+    g = np.load(os.path.join(golden_dir, "models_pipeline.npz"))
+    unet, vae = _tiny(dev, torch.float16)
+    pipe = RollingDepthPipeline(unet, vae, DDIMSchedule(**mu.DDIM_CFG), snippet_batch=4)
+    pipe.empty_text_embed = torch.from_numpy(g["pipe_text"]).to(dev).half()
+    frames = torch.from_numpy(g["pipe_frames"])
+    kw = dict(input_frames=frames, cap_dilation=True, snippet_lengths=[3], init_infer_steps=[1], strides=[1],
+              coalign_kwargs=dict(num_iterations=20), refine_step=2, refine_snippet_len=3, refine_start_dilation=3,
+              verbose=False, max_vae_bs=4)
+    a = pipe.forward(dilations=[1, 3], generator=torch.Generator().manual_seed(0), unload_snippet=False, **kw)
+    b = pipe.forward(dilations=[1, 3], generator=torch.Generator().manual_seed(0), unload_snippet=True, **kw)
+    assert torch.equal(a.depth_pred, b.depth_pred) and torch.equal(a.depth_coaligned, b.depth_coaligned)
+    for x, y in zip(a.snippet_ls, b.snippet_ls):
+        assert torch.equal(x, y) and y.device.type == "cpu"
+    # 10 frames, windows (f, f+4, f+8) for f = 0, 1: frames 2, 3, 6, 7 are in no window
+    kw.update(cap_dilation=False, refine_start_dilation=4)
+    with pytest.raises(AssertionError):
+        pipe.forward(dilations=[1, 3], generator=torch.Generator().manual_seed(0), unload_snippet=False, **kw)
