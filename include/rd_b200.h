@@ -66,6 +66,8 @@ int rd_device_arch(void);
 /* query tiles per CTA: 0 = chosen by grid size (three 128-row tiles on many-wave grids of long sequences, else two),
  * 2 / 3 = force (A/B measurements; the parity tests run both) */
 #define RD_XATTN_TILES(n) (((n) & 3) << 4)
+/* fp32 inputs: 0 = default path, 1 = scalar FFMA kernel, 2 = error-compensated 3xTF32 tcgen05 kernel (A/B, parity tests of both) */
+#define RD_XATTN_F32(n) (((n) & 3) << 14)
 int rd_xattn_fwd(const void* q, const void* k, const void* v, void* o,
                  int B, int H, int Sq, int Sk, int D,
                  int64_t q_sb, int64_t q_ss, int64_t q_sh,

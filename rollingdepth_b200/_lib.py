@@ -25,6 +25,10 @@ def XATTN_TILES(n: int) -> int:
 def XATTN_POLY(n: int) -> int:
     return (n & 0xF) << 8
 
+
+def XATTN_F32(n: int) -> int:
+    return (n & 3) << 14
+
 _DTYPES = {torch.float32: RD_F32, torch.float16: RD_F16, torch.bfloat16: RD_BF16}
 
 

@@ -19,7 +19,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "librd_b200.so")
 OBJ_DIR = os.path.join(HERE, "build")
-SOURCES = ["rd_abi.cu", "align_kernels.cu", "ddim_kernels.cu", "xattn_sm100.cu", "xattn_sm100_q3.cu", "xattn_f32.cu", "norm_kernels.cu"]
+SOURCES = ["rd_abi.cu", "align_kernels.cu", "ddim_kernels.cu", "xattn_sm100.cu", "xattn_sm100_q3.cu", "xattn_f32.cu", "xattn_tf32.cu", "norm_kernels.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

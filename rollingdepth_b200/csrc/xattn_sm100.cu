@@ -379,6 +379,9 @@ int xattn_q3_fwd(const void* q, const void* k, const void* v, void* o, int B, in
 int xattn_f32_launch(const float* q, const float* k, const float* v, float* o, int B, int H, int Sq, int Sk,
                      const int64_t* qs, const int64_t* ks, const int64_t* vs, const int64_t* os, float scale,
                      cudaStream_t st);
+int xattn_tf32_launch(const float* q, const float* k, const float* v, float* o, int B, int H, int Sq, int Sk,
+                      const int64_t* qs, const int64_t* ks, const int64_t* vs, const int64_t* os, float scale,
+                      cudaStream_t st);
 
 template <typename T, int POLY, bool PINGPONG, bool SPLIT>
 static int launch_k(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const XattnParams& prm, dim3 grid,
@@ -396,6 +399,7 @@ static int launch_k(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensor
 }
 
 constexpr int kDefaultPoly = 1;   // polynomial path off by default (attention log)
+constexpr bool kDefaultF32Tensor = false;   // fp32 inputs: scalar FFMA kernel unless RD_XATTN_F32(2) asks for the 3xTF32 one
 
 template <typename T>
 static int launch_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const XattnParams& prm, dim3 grid,
@@ -434,6 +438,11 @@ extern "C" int rd_xattn_fwd(const void* q, const void* k, const void* v, void* o
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == RD_F32) {
         const int64_t qs[3] = {q_sb, q_ss, q_sh}, ks[3] = {k_sb, k_ss, k_sh}, vs[3] = {v_sb, v_ss, v_sh}, os[3] = {o_sb, o_ss, o_sh};
+        // RD_XATTN_F32(1): the scalar FFMA kernel, (2): the 3xTF32 tcgen05 kernel, 0: default
+        const int f32_path = (flags >> 14) & 3;
+        if (f32_path == 2 || (f32_path == 0 && kDefaultF32Tensor))
+            return xattn_tf32_launch((const float*)q, (const float*)k, (const float*)v, (float*)o, B, H, Sq, Sk, qs, ks, vs, os,
+                                     scale, st);
         return xattn_f32_launch((const float*)q, (const float*)k, (const float*)v, (float*)o, B, H, Sq, Sk, qs, ks, vs, os,
                                 scale, st);
     }

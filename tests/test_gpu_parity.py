@@ -142,14 +142,16 @@ def test_xattn_production_shapes_default_flags(B, S, H, what):
     assert torch.equal(out, out2), "the kernel must be deterministic run to run"
 
 
-def test_xattn_fp32_processor_shape_level0():
+@pytest.mark.parametrize("f32_path", [1, 2], ids=["ffma", "3xtf32"])
+def test_xattn_fp32_processor_shape_level0(f32_path):
     """fp32 path (`paper` preset / cfg1) at S = 15552, 5 heads: <= 1e-4 max-abs against a float64 softmax on sampled rows."""
-    from rollingdepth_b200 import ops
+    from rollingdepth_b200 import ops, _lib as L
     dev = _dev()
     S, H = 15552, 5
     g = torch.Generator(device=dev).manual_seed(7)
     q, k, v = [torch.randn(1, S, H * 64, device=dev, dtype=torch.float32, generator=g).view(1, S, H, 64) for _ in range(3)]
-    out = ops.xattn_fwd(q, k, v)
+    out = ops.xattn_fwd(q, k, v, flags=L.XATTN_F32(f32_path))
+    assert torch.isfinite(out).all()
     rows = torch.tensor([0, 77, 5000, S - 1], device=dev)
     for h in (0, 4):
         s = (q[0, rows, h].double() @ k[0, :, h].double().T) * 0.125
@@ -192,13 +194,16 @@ def test_xattn_rejects_bad_arguments():
         ops.xattn_fwd(q.cpu(), q.cpu(), q.cpu())   # no CPU fallback
 
 
-@pytest.mark.parametrize("shape", [(1, 252, 252, 20), (1, 1024, 1024, 5), (2, 130, 67, 3), (1, 500, 2, 5)])
-def test_xattn_fp32_matches_oracle(shape):
-    from rollingdepth_b200 import ops
+@pytest.mark.parametrize("f32_path", [0, 1, 2], ids=["default", "ffma", "3xtf32"])
+@pytest.mark.parametrize("shape", [(1, 252, 252, 20), (1, 1024, 1024, 5), (2, 130, 67, 3), (1, 500, 2, 5), (1, 1, 1, 1), (2, 3072, 3072, 5)])
+def test_xattn_fp32_matches_oracle(shape, f32_path):
+    """fp32 inputs: the scalar FFMA kernel and the error-compensated 3xTF32 tcgen05 kernel, both within the north star's
+    1e-4 max-abs of a float64 softmax."""
+    from rollingdepth_b200 import ops, _lib as L
     dev = _dev()
     B, Sq, Sk, H = shape
     q, k, v = _rand_qkv(B, Sq, Sk, H, torch.float32, dev, seed=3)
-    out = ops.xattn_fwd(q, k, v)
+    out = ops.xattn_fwd(q, k, v, flags=L.XATTN_F32(f32_path))
     ref = oxa.sdpa_ref(q.transpose(1, 2).double(), k.transpose(1, 2).double(), v.transpose(1, 2).double(),
                        acc_dtype=torch.float64).transpose(1, 2)
     assert float((out.double() - ref).abs().max()) <= 1e-4

@@ -105,10 +105,15 @@ def bench_attn_fp32(args):
         q, k, v = [torch.randn(B, S, H * 64, device=dev).view(B, S, H, 64) for _ in range(3)]
         out = torch.empty_like(q)
         flops = 4.0 * B * H * S * S * 64
-        med, _ = time_cuda(lambda: ops.xattn_fwd(q, k, v, out=out), iters=5)
+        from rollingdepth_b200 import _lib as L
+        med, _ = time_cuda(lambda: ops.xattn_fwd(q, k, v, out=out, flags=L.XATTN_F32(1)), iters=5)
+        ref = out.clone()
+        med3, _ = time_cuda(lambda: ops.xattn_fwd(q, k, v, out=out, flags=L.XATTN_F32(2)), iters=5)
+        diff = float((out - ref).abs().max())
         qt, kt, vt = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
         m2, _ = time_cuda(lambda: torch.nn.functional.scaled_dot_product_attention(qt, kt, vt), iters=5)
-        print(json.dumps(dict(bench="xattn_fp32", case=name, S=S, H=H, ms=med, tflops=flops / med / 1e9, torch_sdpa_fp32_ms=m2,
+        print(json.dumps(dict(bench="xattn_fp32", case=name, S=S, H=H, ms=med, tflops=flops / med / 1e9, ms_3xtf32=med3,
+                              tflops_3xtf32=flops / med3 / 1e9, max_abs_3xtf32_vs_ffma=diff, torch_sdpa_fp32_ms=m2,
                               torch_sdpa_fp32_tflops=flops / m2 / 1e9)), flush=True)
 
 
