@@ -399,7 +399,7 @@ static int launch_k(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensor
 }
 
 constexpr int kDefaultPoly = 1;   // polynomial path off by default (attention log)
-constexpr bool kDefaultF32Tensor = false;   // fp32 inputs: scalar FFMA kernel unless RD_XATTN_F32(2) asks for the 3xTF32 one
+constexpr bool kDefaultF32Tensor = true;    // fp32 inputs: the 3xTF32 tcgen05 kernel (xattn_tf32.cu); RD_XATTN_F32(1) = scalar FFMA kernel
 
 template <typename T>
 static int launch_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mv, const XattnParams& prm, dim3 grid,

@@ -8,10 +8,11 @@
 // Same flash-style organisation as the fp16 kernels (xattn_sm100.cu), one 128-row query tile per CTA, 64-key steps:
 //   warps 0-3   softmax: one query row = one TMEM lane per thread; P is split into hi / lo in registers and written to
 //               TMEM (tcgen05.st) as the A operand of the PV products
-//   warps 4-7   operand splitters: the raw fp32 tiles land in shared memory by TMA; these warps rewrite them in place as
-//               hi and write lo beside them (element-wise, so the SWIZZLE_128B layout is preserved), then
-//               fence.proxy.async + mbarrier so that tcgen05.mma may read them
-//   warp 8      tcgen05.mma issuer (kind::tf32, cta_group::1; owns TMEM): 24 MMAs per step for S, 48 for O
+//   warps 4-7   operand splitters: the raw fp32 tiles land in shared memory by TMA; these warps rewrite Q and K in place as
+//               hi and write lo beside them (element-wise, so the SWIZZLE_128B layout is preserved), and TRANSPOSE V into
+//               K-major [channel][key] hi / lo tiles (kind::tf32 takes no MN-major B operand: measured, the MMA is a no-op),
+//               then fence.proxy.async + mbarrier so that tcgen05.mma may read them
+//   warp 8      tcgen05.mma issuer (kind::tf32, cta_group::1; owns TMEM): 24 MMAs per step for S, 24 for O
 //   warp 9      TMA producer: Q once, K/V tiles of 64 keys through a 2-stage ring (fp32 rows of 64 = two 128-byte
 //               swizzle atoms of 32 channels each: two boxes per tile)
 // TMEM: S fp32 64 columns, O 64, Phi 64, Plo 64.  Shared memory: Q hi/lo 64 KB + 2 x (K hi/lo + V hi/lo) 128 KB.
@@ -49,13 +50,17 @@ struct Smem {
     static constexpr int stage0 = q_lo + kQBytes;
     static constexpr int k_hi = 0, k_lo = kKBytes, v_hi = 2 * kKBytes, v_lo = 3 * kKBytes;   // offsets inside a stage
     static constexpr int stage_bytes = 4 * kKBytes;
-    static constexpr int bars = stage0 + kStages * stage_bytes;       // 16 x 8 bytes
-    static constexpr int tmem_ptr = bars + 16 * 8;
+    static constexpr int bars = stage0 + kStages * stage_bytes;       // 24 x 8 bytes
+    static constexpr int tmem_ptr = bars + 24 * 8;
     static constexpr int bytes = tmem_ptr + 16;
 };
-constexpr int Q_RAW = 0, Q_SPLIT = 1, KV_RAW = 2, KV_SPLIT = KV_RAW + kStages, KV_EMPTY = KV_SPLIT + kStages,
-              S_FULL = KV_EMPTY + kStages, S_FREE = S_FULL + 1, P_FULL = S_FREE + 1, O_READY = P_FULL + 1;
-static_assert(O_READY < 16, "barrier table too small");
+// K and V travel through separate 2-stage rings: a K stage is free again as soon as QK^T of its step has completed, a V
+// stage only after PV of its step -- with one ring for both the reload of step j+2 waited for PV(j) and every step paid the
+// TMA + split latency in series (measured: 100 TFLOP/s; the MMA work of a step is a third of that)
+constexpr int Q_RAW = 0, Q_SPLIT = 1, K_RAW = 2, K_SPLIT = K_RAW + kStages, K_EMPTY = K_SPLIT + kStages,
+              V_RAW = K_EMPTY + kStages, V_SPLIT = V_RAW + kStages, V_EMPTY = V_SPLIT + kStages,
+              S_FULL = V_EMPTY + kStages, S_FREE = S_FULL + 1, P_FULL = S_FREE + 1, O_READY = P_FULL + 1;
+static_assert(O_READY < 24, "barrier table too small");
 
 struct Params {
     float* o;
@@ -102,6 +107,39 @@ __device__ __forceinline__ void split_region(uint8_t* hi, uint8_t* lo, int n16, 
     }
 }
 
+// V tile: raw [64 keys][64 channels] as TMA left it at `v` (two SWIZZLE_128B atoms of 32 channels, 128-byte rows = keys)
+// -> V^T hi at `v` and V^T lo at `lo`, each [64 channels][64 keys] as two atoms of 32 keys (128-byte rows = channels): the
+// K-major B operand of O += P V.  Thread (warp w, lane): channel 32 (w & 1) + lane, keys 32 (w >> 1) .. + 31; every thread
+// pulls its 32 raw values into registers, the 128 splitter threads meet on a named barrier (the raw tile is overwritten in
+// place), then each writes eight 16-byte chunks of hi and of lo.  Swizzle: 16-byte chunk index ^= (row & 7).
+__device__ __forceinline__ void transpose_split_v(uint8_t* v, uint8_t* lo, int tid) {
+    const int lane = tid & 31, w = tid >> 5;
+    const int ch = 32 * (w & 1) + lane, a_in = w & 1, a_out = w >> 1;
+    const uint8_t* in = v + a_in * kAtomK + (lane & 3) * 4;
+    const int chunk_in = lane >> 2;
+    uint32_t raw[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const int key = 32 * a_out + i;
+        raw[i] = *reinterpret_cast<const uint32_t*>(in + key * 128 + ((chunk_in ^ (key & 7)) << 4));
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    uint8_t* oh = v + a_out * kAtomK + ch * 128;
+    uint8_t* ol = lo + a_out * kAtomK + ch * 128;
+#pragma unroll
+    for (int c4 = 0; c4 < 8; ++c4) {
+        uint4 h, l;
+        h.x = raw[4 * c4] & kHiMask; h.y = raw[4 * c4 + 1] & kHiMask; h.z = raw[4 * c4 + 2] & kHiMask; h.w = raw[4 * c4 + 3] & kHiMask;
+        l.x = __float_as_uint(__uint_as_float(raw[4 * c4]) - __uint_as_float(h.x));
+        l.y = __float_as_uint(__uint_as_float(raw[4 * c4 + 1]) - __uint_as_float(h.y));
+        l.z = __float_as_uint(__uint_as_float(raw[4 * c4 + 2]) - __uint_as_float(h.z));
+        l.w = __float_as_uint(__uint_as_float(raw[4 * c4 + 3]) - __uint_as_float(h.w));
+        const int off = (c4 ^ (ch & 7)) << 4;
+        *reinterpret_cast<uint4*>(oh + off) = h;
+        *reinterpret_cast<uint4*>(ol + off) = l;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 xattn_tf32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                   const __grid_constant__ CUtensorMap tm_v, const Params prm) {
@@ -119,9 +157,12 @@ xattn_tf32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         mbar_init(&bars[Q_RAW], 1);
         mbar_init(&bars[Q_SPLIT], 4);            // one elected lane per splitter warp
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(&bars[KV_RAW + s], 1);
-            mbar_init(&bars[KV_SPLIT + s], 4);
-            mbar_init(&bars[KV_EMPTY + s], 1);   // tcgen05.commit after PV of the step
+            mbar_init(&bars[K_RAW + s], 1);
+            mbar_init(&bars[K_SPLIT + s], 4);
+            mbar_init(&bars[K_EMPTY + s], 1);    // tcgen05.commit after QK^T of the step
+            mbar_init(&bars[V_RAW + s], 1);
+            mbar_init(&bars[V_SPLIT + s], 4);
+            mbar_init(&bars[V_EMPTY + s], 1);    // tcgen05.commit after PV of the step
         }
         mbar_init(&bars[S_FULL], 1);
         mbar_init(&bars[S_FREE], 4);             // one elected lane per softmax warp
@@ -152,25 +193,28 @@ xattn_tf32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             for (int j = 0; j < n_steps; ++j) {
                 const int st = j % kStages;
                 uint8_t* sb = smem + Smem::stage0 + st * Smem::stage_bytes;
-                mbar_wait(&bars[KV_EMPTY + st], ((j / kStages) & 1) ^ 1);
-                mbar_arrive_expect_tx(&bars[KV_RAW + st], 2 * kKBytes);
-                tma_load_4d(sb + Smem::k_hi, &tm_k, &bars[KV_RAW + st], 0, j * kBK, head, batch);
-                tma_load_4d(sb + Smem::k_hi + kAtomK, &tm_k, &bars[KV_RAW + st], 32, j * kBK, head, batch);
-                tma_load_4d(sb + Smem::v_hi, &tm_v, &bars[KV_RAW + st], 0, j * kBK, head, batch);
-                tma_load_4d(sb + Smem::v_hi + kAtomK, &tm_v, &bars[KV_RAW + st], 32, j * kBK, head, batch);
+                const uint32_t ph = ((j / kStages) & 1) ^ 1;
+                mbar_wait(&bars[K_EMPTY + st], ph);
+                mbar_arrive_expect_tx(&bars[K_RAW + st], kKBytes);
+                tma_load_4d(sb + Smem::k_hi, &tm_k, &bars[K_RAW + st], 0, j * kBK, head, batch);
+                tma_load_4d(sb + Smem::k_hi + kAtomK, &tm_k, &bars[K_RAW + st], 32, j * kBK, head, batch);
+                mbar_wait(&bars[V_EMPTY + st], ph);
+                mbar_arrive_expect_tx(&bars[V_RAW + st], kKBytes);
+                tma_load_4d(sb + Smem::v_hi, &tm_v, &bars[V_RAW + st], 0, j * kBK, head, batch);
+                tma_load_4d(sb + Smem::v_hi + kAtomK, &tm_v, &bars[V_RAW + st], 32, j * kBK, head, batch);
             }
         }
     } else if (warp == kMmaWarp) {
         // ===================================================== MMA issuer (uniform control flow, elected lane issues)
         const bool leader = elect_one();
         constexpr uint32_t idesc_qk = make_idesc_tf32(0, kBM, kBK);      // S[128, 64 keys] = Q K^T, both K-major
-        constexpr uint32_t idesc_pv = make_idesc_tf32(1, kBM, 32);       // O[128, 32 channels] += P V, B = V MN-major
+        constexpr uint32_t idesc_pv = make_idesc_tf32(0, kBM, kD);       // O[128, 64 channels] += P V^T^T, B = V^T K-major
         const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
 
         auto issue_qk = [&](int j) {
             const int st = j % kStages;
             uint8_t* sb = smem + Smem::stage0 + st * Smem::stage_bytes;
-            mbar_wait(&bars[KV_SPLIT + st], (j / kStages) & 1);
+            mbar_wait(&bars[K_SPLIT + st], (j / kStages) & 1);
             if (j > 0) mbar_wait(&bars[S_FREE], (j - 1) & 1);            // softmax(j-1) has S in registers
             tc_fence_after();
             if (leader) {
@@ -190,6 +234,7 @@ xattn_tf32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
                         }
                     }
                 }
+                mma_commit(&bars[K_EMPTY + st]);
                 mma_commit(&bars[S_FULL]);
             }
             __syncwarp();
@@ -201,25 +246,26 @@ xattn_tf32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
             if (j + 1 < n_steps) issue_qk(j + 1);
             const int st = j % kStages;
             uint8_t* sb = smem + Smem::stage0 + st * Smem::stage_bytes;
+            mbar_wait(&bars[V_SPLIT + st], (j / kStages) & 1);
             mbar_wait(&bars[P_FULL], j & 1);
             tc_fence_after();
             if (leader) {
+                uint32_t acc = j > 0 ? 1u : 0u;
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {                            // output channels [32 h, 32 h + 32)
-                    uint32_t acc = j > 0 ? 1u : 0u;
+                for (int term = 0; term < 3; ++term) {                   // hi*hi, hi*lo, lo*hi
+                    const uint32_t pa = tm + (term == 2 ? kColPlo : kColPhi);
+                    const uint8_t* vb = sb + (term == 1 ? Smem::v_lo : Smem::v_hi);
 #pragma unroll
-                    for (int term = 0; term < 3; ++term) {               // hi*hi, hi*lo, lo*hi
-                        const uint32_t pa = tm + (term == 2 ? kColPlo : kColPhi);
-                        const uint8_t* vb = sb + (term == 1 ? Smem::v_lo : Smem::v_hi) + h * kAtomK;
-                        const uint64_t dv = make_smem_desc_sw128(smem_u32(vb), 16, 1024);
+                    for (int a = 0; a < 2; ++a) {                        // the two 32-key swizzle atoms of the transposed V tile
+                        const uint64_t dv = make_smem_desc_sw128(smem_u32(vb + a * kAtomK), 16, 1024);
 #pragma unroll
-                        for (int kk = 0; kk < kBK / 8; ++kk) {           // 8 keys = 8 rows of 128 bytes per MMA
-                            mma_tf32_ts(tm + kColO + 32 * h, pa + 8 * kk, dv + (uint64_t)(64 * kk), idesc_pv, acc);
+                        for (int kk = 0; kk < 4; ++kk) {                 // 8 keys = 32 bytes per MMA
+                            mma_tf32_ts(tm + kColO, pa + a * 32 + 8 * kk, dv + 2 * kk, idesc_pv, acc);
                             acc = 1;
                         }
                     }
                 }
-                mma_commit(&bars[KV_EMPTY + st]);
+                mma_commit(&bars[V_EMPTY + st]);
                 mma_commit(&bars[O_READY]);
             }
             __syncwarp();
@@ -235,12 +281,16 @@ xattn_tf32_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
         for (int j = 0; j < n_steps; ++j) {
             const int st = j % kStages;
             uint8_t* sb = smem + Smem::stage0 + st * Smem::stage_bytes;
-            mbar_wait(&bars[KV_RAW + st], (j / kStages) & 1);
+            mbar_wait(&bars[K_RAW + st], (j / kStages) & 1);
             split_region(sb + Smem::k_hi, sb + Smem::k_lo, kKBytes / 16, tid);
-            split_region(sb + Smem::v_hi, sb + Smem::v_lo, kKBytes / 16, tid);
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[KV_SPLIT + st]);
+            if (lane == 0) mbar_arrive(&bars[K_SPLIT + st]);
+            mbar_wait(&bars[V_RAW + st], (j / kStages) & 1);
+            transpose_split_v(sb + Smem::v_hi, sb + Smem::v_lo, tid);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[V_SPLIT + st]);
         }
     } else {
         // ===================================================== softmax warps (one query row per thread)
