@@ -111,3 +111,24 @@ def test_unsupported_config_values_are_refused():
                 UNet2DConditionModel(**mu.SD2_UNET, **bad)
         with pytest.raises(NotImplementedError):
             AutoencoderKL(**{k: v for k, v in mu.SD_VAE.items() if not k.endswith("block_types")}, mid_block_add_attention=False)
+
+
+@pytest.mark.parametrize("H,W", [(40, 48), (50, 70), (37, 91), (432, 768)])
+def test_latent_size_formula_matches_the_encoder(H, W):
+    """`RollingDepthPipeline._latent_hw` (used to size the all-gather buffers, also on ranks that own no frame) against
+    the shape the VAE encoder really produces, including sizes that are not multiples of the total stride: every level
+    pads (0, 1, 0, 1) and applies a 3x3 stride-2 convolution without padding = floor(size / 2)."""
+    from rollingdepth_b200.pipeline import RollingDepthPipeline
+    from rollingdepth_b200.scheduler import DDIMSchedule
+    unet, vae = _tiny()
+    pipe = RollingDepthPipeline(unet, vae, DDIMSchedule(**mu.DDIM_CFG), install_processor=False)
+    if H * W < 10000:
+        with torch.no_grad():
+            lat = vae.quant_conv(vae.encoder(torch.zeros(1, 3, H, W)))
+        assert tuple(lat.shape[-2:]) == pipe._latent_hw(H, W)
+        dec_hw = pipe._decoded_hw(*lat.shape[-2:])
+        with torch.no_grad():
+            dec = vae.decoder(vae.post_quant_conv(lat[:, :4]))
+        assert tuple(dec.shape[-2:]) == dec_hw
+    else:
+        assert pipe._latent_hw(H, W) == (H // 2, W // 2)        # the tiny VAE has one stride-2 level
