@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 GPU-box visit: -m gpu suite, smoke, bench.py (fast, stage times), microbenchmarks, ncu launch list.
-# usage: tools/gpu_visit2.sh TAG [tests] [bench] [mb] [launches] [ncu_xattn] [ncu_coalign] [full]
+# usage: tools/visits/gpu_visit2.sh TAG [tests] [bench] [mb] [launches] [ncu_xattn] [ncu_coalign] [full]
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
