@@ -346,7 +346,8 @@ def workload_config(preset, world, args=None):
            "l2": "inputs (>= 300 MB of frames/latents/snippets per step) exceed the 126 MB L2; no explicit flush"}
     if args is not None:
         cfg.update({"snippet_batch": args.snippet_batch, "max_vae_bs": args.max_vae_bs, "channels_last": bool(args.channels_last),
-                    "fused_norm": bool(args.fused_norm), "cudnn_benchmark": bool(args.cudnn_benchmark)})
+                    "fused_norm": bool(args.fused_norm), "cudnn_benchmark": bool(args.cudnn_benchmark),
+                    "subpixel_upsample_conv": bool(args.subpixel)})
     return cfg
 
 
@@ -388,6 +389,8 @@ def run_ours(args):
 
     unet, vae = build_models(dev, dtype)
     torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)
+    from rollingdepth_b200.sd2.layers import Upsample2D
+    Upsample2D.subpixel = bool(args.subpixel)
     if dtype == torch.float32:      # the fp32 presets are tolerance checks against the reference's true-fp32 path
         torch.backends.cudnn.allow_tf32 = False
         torch.backends.cuda.matmul.allow_tf32 = False
@@ -540,6 +543,7 @@ if __name__ == "__main__":
     ap.add_argument("--channels-last", type=int, default=1)
     ap.add_argument("--fused-norm", type=int, default=1)
     ap.add_argument("--cudnn-benchmark", type=int, default=1)
+    ap.add_argument("--subpixel", type=int, default=1, help="0: Upsample2D as nearest upsampling + 3x3 convolution (A/B)")
     ap.add_argument("--coalign-mode", default="replicated", choices=["replicated", "allreduce"],
                     help="multi-GPU only: replicated optimiser or frame-sharded with a per-iteration all-reduce")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -226,6 +226,15 @@ int rd_bias_residual_nhwc(const void* x, const void* bias, const void* vec, cons
 int rd_upsample_nearest_nhwc(const void* x, void* y, int N, int Hi, int Wi, int Ho, int Wo, int C,
                              rd_dtype dtype, void* stream);
 
+/* Sub-pixel form of Upsample2D (upsampling.py Upsample2D.forward: nearest 2x upsampling, then the 3x3 convolution): the
+ * convolution runs on the low-resolution tensor as one 2x2 convolution (padding 1) with 4 C output channels -- channel block
+ * 2a + b holds output phase (a, b), its four tap weights are the sums of the 3x3 taps that read the same source pixel -- and this
+ * entry point interleaves the phases and adds the bias:
+ *     y[n, 2i + a, 2j + b, c] = t[n, i + a, j + b, (2a + b) C + c] + bias[c]
+ * for t = [N, H + 1, W + 1, 4 C] and y = [N, 2 H, 2 W, C], both NHWC; bias may be NULL. */
+int rd_phase_shuffle_bias_nhwc(const void* t, const void* bias, void* y, int N, int H, int W, int C,
+                               rd_dtype dtype, void* stream);
+
 /* GEGLU gate of the transformer feed-forward (diffusers/src/diffusers/models/activations.py GEGLU.forward, called from
  * attention.py FeedForward): y[m, d] = proj[m, d] * gelu(proj[m, D + d]) for a contiguous [M, 2 D] projection; exact
  * (erf) GELU, rounding as torch (gelu in fp32 -> dtype, product in fp32 -> dtype).  One pass instead of gelu + mul. */

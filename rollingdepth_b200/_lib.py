@@ -97,6 +97,7 @@ SIGNATURES = {
     "rd_groupnorm_nhwc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _I, _P, _I64, _P]),
     "rd_bias_residual_nhwc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "rd_upsample_nearest_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),
+    "rd_phase_shuffle_bias_nhwc": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P]),
     "rd_geglu": (_I, [_P, _P, _I64, _I, _I, _P]),
     "rd_softmax_rows": (_I, [_P, _P, _I64, _I, _F, _I, _P]),
     "rd_layernorm": (_I, [_P, _P, _P, _P, _I64, _I, _F, _I, _P]),

@@ -313,6 +313,62 @@ __global__ void __launch_bounds__(256) upsample_nearest_nhwc_kernel(const UpPara
     }
 }
 
+// Sub-pixel form of "nearest 2x upsampling followed by a 3x3 convolution" (upsampling.py Upsample2D.forward: F.interpolate
+// (scale_factor=2, mode="nearest") then self.conv): output pixel (2i + a, 2j + b) only ever sees a 2x2 neighbourhood of the
+// low-resolution input, so the convolution runs on the low-resolution tensor as ONE 2x2 convolution (padding 1) with
+// 4 C output channels (channel block 2a + b = phase (a, b), tap weights = sums of the 3x3 taps that fall on the same source
+// pixel; 16 instead of 36 multiply-adds per source pixel and output channel) and this kernel interleaves the four phases
+// and adds the bias:   y[n, 2i + a, 2j + b, c] = t[n, i + a, j + b, (2a + b) C + c] + bias[c],   t = [N, H + 1, W + 1, 4 C].
+struct PhaseParams { const void* t; const void* bias; void* y; int N, H, W, CV; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) phase_shuffle_bias_kernel(const PhaseParams p) {
+    constexpr int VN = GnVec<T>::N;
+    constexpr int U = 4;                                   // independent 16-byte loads in flight per thread
+    const int Ho = 2 * p.H, Wo = 2 * p.W, Hp = p.H + 1, Wp = p.W + 1;
+    const long long total = (long long)p.N * Ho * Wo * p.CV;
+    const T* tin = reinterpret_cast<const T*>(p.t);
+    const T* bias = reinterpret_cast<const T*>(p.bias);
+    T* yout = reinterpret_cast<T*>(p.y);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
+        uint4 in[U];
+        int cvs[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            if (i < total) {
+                const int cv = (int)(i % p.CV);
+                long long r = i / p.CV;
+                const int wo = (int)(r % Wo); r /= Wo;
+                const int ho = (int)(r % Ho);
+                const int n = (int)(r / Ho);
+                const int a = ho & 1, b = wo & 1;
+                const long long src = ((((long long)n * Hp + (ho >> 1) + a) * Wp + (wo >> 1) + b) * 4 + (2 * a + b)) * p.CV + cv;
+                in[u] = ldg_stream16(tin + src * VN);
+                cvs[u] = cv;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * stride;
+            if (i < total) {
+                if (bias) {
+                    float f[VN], bv[VN];
+                    gn_unpack<T>(in[u], f);
+                    gn_unpack<T>(__ldg(reinterpret_cast<const uint4*>(bias) + cvs[u]), bv);
+                    alignas(16) T o[VN];
+#pragma unroll
+                    for (int k = 0; k < VN; ++k) o[k] = Cvt<T>::from_f(f[k] + bv[k]);
+                    *reinterpret_cast<uint4*>(yout + i * VN) = *reinterpret_cast<const uint4*>(o);
+                } else {
+                    *reinterpret_cast<uint4*>(yout + i * VN) = in[u];
+                }
+            }
+        }
+    }
+}
+
 // GEGLU gate of the transformer feed-forward (diffusers/src/diffusers/models/activations.py GEGLU.forward):
 // proj [M, 2 D] -> out [M, D] = proj[:, :D] * gelu(proj[:, D:]); one pass instead of torch's gelu + mul over two
 // strided halves.  Rounding as torch: gelu in fp32 -> T, product in fp32 -> T.
@@ -592,6 +648,27 @@ int rd_upsample_nearest_nhwc(const void* x, void* y, int N, int Hi, int Wi, int 
     const int blocks = (int)(want > (long long)num_sms() * 32 ? (long long)num_sms() * 32 : want);
     upsample_nearest_nhwc_kernel<uint4><<<blocks, 256, 0, (cudaStream_t)stream>>>(p);
     RD_LAUNCH_CHECK("upsample_nearest_nhwc_kernel");
+    return RD_OK;
+}
+
+int rd_phase_shuffle_bias_nhwc(const void* t, const void* bias, void* y, int N, int H, int W, int C, rd_dtype dtype,
+                               void* stream) {
+    RD_CHECK_ARG(t && y && N >= 1 && H >= 1 && W >= 1 && C >= 1, "bad argument");
+    RD_CHECK_ARG(dtype == RD_F32 || dtype == RD_F16 || dtype == RD_BF16, "bad dtype");
+    const int es = dtype == RD_F32 ? 4 : 2, VN = 16 / es;
+    if (C % VN != 0) { set_error("C=%d is not a multiple of the 16-byte vector width", C); return RD_ERR_UNSUPPORTED; }
+    RD_CHECK_ARG((((uintptr_t)t | (uintptr_t)y | (uintptr_t)bias) & 15) == 0, "pointers must be 16-byte aligned");
+    PhaseParams p{t, bias, y, N, H, W, C / VN};
+    const long long total = (long long)N * 4 * H * W * p.CV;
+    const long long want = (total + 4 * 256 - 1) / (4 * 256);
+    const int blocks = (int)(want > (long long)num_sms() * 16 ? (long long)num_sms() * 16 : want);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case RD_F32: phase_shuffle_bias_kernel<float><<<blocks, 256, 0, st>>>(p); break;
+        case RD_F16: phase_shuffle_bias_kernel<__half><<<blocks, 256, 0, st>>>(p); break;
+        default:     phase_shuffle_bias_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>(p); break;
+    }
+    RD_LAUNCH_CHECK("phase_shuffle_bias_kernel");
     return RD_OK;
 }
 

@@ -156,6 +156,25 @@ def upsample_nearest_nhwc(x: torch.Tensor, size) -> torch.Tensor:
     return y
 
 
+def phase_shuffle_bias_nhwc(t: torch.Tensor, bias, H: int, W: int) -> torch.Tensor:
+    """y[n, c, 2i + a, 2j + b] = t[n, (2a + b) C + c, i + a, j + b] + bias[c] for a channels_last t of shape
+    [N, 4 C, H + 1, W + 1] (the four phases of a sub-pixel Upsample2D convolution) -> channels_last [N, C, 2 H, 2 W]."""
+    L.require_cuda(t)
+    if t.dim() != 4 or not t.is_contiguous(memory_format=torch.channels_last):
+        raise L.RdError("expected a channels_last [N, 4C, H+1, W+1] tensor")
+    N, C4, Hp, Wp = t.shape
+    if C4 % 4 != 0 or Hp != H + 1 or Wp != W + 1:
+        raise L.RdError(f"phase tensor {tuple(t.shape)} does not match H={H}, W={W}")
+    Cc = C4 // 4
+    if bias is not None and (bias.dtype != t.dtype or bias.numel() != Cc or not bias.is_contiguous()):
+        raise L.RdError("bias must be a contiguous [C] tensor of the activation dtype")
+    y = torch.empty((N, Cc, 2 * H, 2 * W), dtype=t.dtype, device=t.device, memory_format=torch.channels_last)
+    L.call("rd_phase_shuffle_bias_nhwc", t.device, L.ptr(t), L.ptr(bias) if bias is not None else None, L.ptr(y),
+           N, H, W, Cc, L.dtype_code(t.dtype), L.stream_ptr(t.device))
+    L.count_launches(1)
+    return y
+
+
 def geglu(proj: torch.Tensor) -> torch.Tensor:
     """proj[..., :D] * gelu(proj[..., D:]) for a contiguous [..., 2 D] projection (one fused pass)."""
     L.require_cuda(proj)

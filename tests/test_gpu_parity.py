@@ -642,3 +642,59 @@ def test_layernorm_matches_torch_fp32(M, C, dtype, tol):
     assert float((y.float() - ref).abs().max()) <= tol * max(1.0, float(ref.abs().max()))
     lib = torch.nn.functional.layer_norm(x, (C,), w, b, 1e-5)
     assert float((y.float() - lib.float()).abs().max()) <= tol * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+def test_phase_shuffle_bias_nhwc_bit_exact(dtype):
+    """rd_phase_shuffle_bias_nhwc against its index formula (include/rd_b200.h) evaluated by torch: a pure gather plus one
+    fp32 add and rounding -> identical bits; with and without bias, odd sizes, one-pixel input."""
+    from rollingdepth_b200 import ops
+    from test_models_cpu import phase_shuffle_reference
+    dev = _dev()
+    g = torch.Generator().manual_seed(9)
+    for (N, C, H, W) in [(2, 64, 5, 7), (1, 8, 1, 1), (3, 320, 13, 6), (1, 128, 54, 96)]:
+        t = torch.randn(N, 4 * C, H + 1, W + 1, generator=g).to(dtype).to(dev).contiguous(memory_format=torch.channels_last)
+        b = torch.randn(C, generator=g).to(dtype).to(dev)
+        for bias in (b, None):
+            y = ops.phase_shuffle_bias_nhwc(t, bias, H, W)
+            assert y.shape == (N, C, 2 * H, 2 * W) and y.is_contiguous(memory_format=torch.channels_last)
+            assert torch.equal(y, phase_shuffle_reference(t, bias, H, W))
+    with pytest.raises(Exception):
+        ops.phase_shuffle_bias_nhwc(t, None, H + 1, W)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 5e-6), (torch.float16, 3e-3), (torch.bfloat16, 2.5e-2)])
+def test_upsample2d_subpixel_matches_upsample_then_conv(dtype, tol):
+    """Upsample2D in sub-pixel form (2x2 phase convolution + rd_phase_shuffle_bias_nhwc) against the reference's order of
+    operations (upsampling.py Upsample2D.forward: F.interpolate nearest, then conv) evaluated by torch in fp32 on the same
+    weights: relative to the output range, within the rounding of the dtype; explicit non-2x sizes keep the nearest + conv path."""
+    from rollingdepth_b200.sd2.layers import Upsample2D
+    dev = _dev()
+    torch.manual_seed(5)
+    torch.backends.cudnn.allow_tf32 = False          # torch allows TF32 convolutions by default: the fp32 case means fp32
+    for (N, C, H, W) in [(2, 64, 9, 12), (1, 320, 14, 24), (3, 128, 27, 48)]:
+        m = Upsample2D(C).to(dev, dtype).to(memory_format=torch.channels_last).eval()
+        x = torch.randn(N, C, H, W, device=dev).to(dtype).contiguous(memory_format=torch.channels_last)
+        with torch.no_grad():
+            ref = torch.nn.functional.conv2d(torch.nn.functional.interpolate(x.float(), scale_factor=2.0, mode="nearest"),
+                                             m.conv.weight.float(), m.conv.bias.float(), 1, 1)
+            m.fused = True
+            m.conv.fused = True
+            got = m(x)
+            assert got.shape == ref.shape and got.dtype == dtype
+            scale = float(ref.abs().max())
+            assert float((got.float() - ref).abs().max()) <= tol * scale
+            m.subpixel = False
+            old = m(x)
+            assert float((old.float() - ref).abs().max()) <= tol * scale
+            odd = m(x, output_size=(2 * H - 1, 2 * W - 1))          # UNet levels of odd size pass an explicit size
+            m.subpixel = True
+            assert torch.equal(odd, m(x, output_size=(2 * H - 1, 2 * W - 1)))
+            # weights changed in place -> the cached phase kernels are rebuilt
+            m.conv.weight.mul_(2.0)
+            got2 = m(x)
+            ref2 = torch.nn.functional.conv2d(torch.nn.functional.interpolate(x.float(), scale_factor=2.0, mode="nearest"),
+                                              m.conv.weight.float(), m.conv.bias.float(), 1, 1)
+            assert float((got2.float() - ref2).abs().max()) <= tol * float(ref2.abs().max())

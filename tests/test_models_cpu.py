@@ -7,6 +7,7 @@ import os
 import numpy as np
 import pytest
 import torch
+import torch.nn.functional as F
 
 import model_utils as mu
 from oracle import pipeline as opipe
@@ -132,3 +133,32 @@ def test_latent_size_formula_matches_the_encoder(H, W):
         assert tuple(dec.shape[-2:]) == dec_hw
     else:
         assert pipe._latent_hw(H, W) == (H // 2, W // 2)        # the tiny VAE has one stride-2 level
+
+
+def phase_shuffle_reference(t, bias, H, W):
+    """torch restatement of rd_phase_shuffle_bias_nhwc (include/rd_b200.h)."""
+    C = t.shape[1] // 4
+    y = t.new_empty(t.shape[0], C, 2 * H, 2 * W)
+    for a in range(2):
+        for b in range(2):
+            y[:, :, a::2, b::2] = t[:, (2 * a + b) * C:(2 * a + b + 1) * C, a:a + H, b:b + W]
+    if bias is not None:
+        y = (y.float() + bias.float().view(1, -1, 1, 1)).to(t.dtype) if t.dtype != torch.float64 else y + bias.view(1, -1, 1, 1)
+    return y
+
+
+@pytest.mark.parametrize("H,W", [(1, 1), (6, 9), (7, 4)])
+def test_subpixel_upsample_convolution_is_the_same_linear_map(H, W):
+    """Upsample2D in sub-pixel form (one 2x2 convolution with the four phase kernels + phase interleave) against
+    F.interpolate(nearest, 2x) + the 3x3 convolution (upsampling.py Upsample2D.forward) in float64: identical up to
+    summation order, borders included."""
+    from rollingdepth_b200.sd2.layers import subpixel_phase_weights
+    g = torch.Generator().manual_seed(H * 31 + W)
+    x = torch.randn(2, 5, H, W, dtype=torch.float64, generator=g)
+    w = torch.randn(7, 5, 3, 3, dtype=torch.float64, generator=g)
+    bias = torch.randn(7, dtype=torch.float64, generator=g)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), w, bias, 1, 1)
+    pw = subpixel_phase_weights(w)
+    assert pw.shape == (28, 5, 2, 2)
+    got = phase_shuffle_reference(F.conv2d(x, pw, None, 1, 1), bias, H, W)
+    assert float((got - ref).abs().max()) < 1e-12

@@ -199,9 +199,57 @@ def bench_gn(args):
                               GBs=3 * nbytes / med / 1e6, frac_of_hbm=3 * nbytes / med / 1e6 / hbm, peak_src=src)), flush=True)
 
 
+def bench_upconv(args):
+    """Upsample2D (nearest 2x + 3x3 convolution + bias): the upsample-then-convolve form against the sub-pixel form (one 2x2
+    cuDNN convolution on the low-resolution tensor + rd_phase_shuffle_bias_nhwc), on the VAE-decoder and UNet shapes of the
+    fast preset.  Also times the im2col + cuBLAS GEMM form of the same 2x2 convolution (torch ops) as a probe."""
+    import torch.nn.functional as F
+    from rollingdepth_b200.sd2.layers import Upsample2D
+    dev = torch.device("cuda:0")
+    torch.backends.cudnn.benchmark = True
+    dtype = torch.float32 if args.full else torch.float16
+    if dtype == torch.float32:
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    for name, N, H, W, Cc in [("dec up0 12x54x96x512", 12, 54, 96, 512), ("dec up1 12x108x192x512", 12, 108, 192, 512),
+                              ("dec up2 12x216x384x256", 12, 216, 384, 256), ("unet up0 48x7x12x1280", 48, 7, 12, 1280),
+                              ("unet up2 48x27x48x640", 48, 27, 48, 640)]:
+        torch.manual_seed(0)
+        m = Upsample2D(Cc).to(dev, dtype).to(memory_format=torch.channels_last).eval()
+        m.conv.fused = True
+        m.fused = True
+        x = torch.randn(N, Cc, H, W, device=dev, dtype=dtype).contiguous(memory_format=torch.channels_last)
+        with torch.no_grad():
+            m.subpixel = False
+            ref = m(x)
+            old, _ = time_cuda(lambda: m(x))
+            m.subpixel = True
+            got = m(x)
+            new, _ = time_cuda(lambda: m(x))
+            pw = m.phase_weight()
+            conv_only, _ = time_cuda(lambda: F.conv2d(x, pw, None, 1, 1))
+            conv3_only, _ = time_cuda(lambda: F.conv2d(ref, m.conv.weight, None, 1, 1))
+            w2 = pw.permute(0, 2, 3, 1).reshape(4 * Cc, 4 * Cc).contiguous()           # [4C out, (u, v, c)]
+
+            def gemm_form():
+                xp = F.pad(x.permute(0, 2, 3, 1), (0, 0, 1, 1, 1, 1))                      # [N, H+2, W+2, C]
+                cols = torch.cat([xp[:, u:u + H + 1, v:v + W + 1] for u in (0, 1) for v in (0, 1)], dim=-1)
+                return cols.reshape(-1, 4 * Cc) @ w2.t()
+            gm, _ = time_cuda(gemm_form)
+            only_gemm_in = torch.randn(N * (H + 1) * (W + 1), 4 * Cc, device=dev, dtype=dtype)
+            g_only, _ = time_cuda(lambda: only_gemm_in @ w2.t())
+        flops36 = 2.0 * N * 4 * H * W * Cc * Cc * 9
+        print(json.dumps(dict(bench="upsample2d", case=name, dtype=str(dtype), upsample_conv_bias_ms=old, subpixel_ms=new,
+                              speedup=old / new, conv3x3_only_ms=conv3_only, conv3x3_TFLOPs=flops36 / conv3_only / 1e9,
+                              conv2x2_only_ms=conv_only, conv2x2_TFLOPs=flops36 * 16 / 36 / conv_only / 1e9,
+                              im2col_gemm_ms=gm, gemm_only_ms=g_only,
+                              max_abs_diff=float((got.float() - ref.float()).abs().max()),
+                              ref_absmax=float(ref.float().abs().max()))), flush=True)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["attn", "attn_fp32", "align", "gn"])
+    ap.add_argument("what", choices=["attn", "attn_fp32", "align", "gn", "upconv"])
     ap.add_argument("--full", action="store_true")
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--iters", type=int, default=200)
@@ -209,4 +257,4 @@ if __name__ == "__main__":
     ap.add_argument("--only", default="")
     ap.add_argument("--no-sdpa", action="store_true", help="skip the torch SDPA comparators")
     a = ap.parse_args()
-    {"attn": bench_attn, "attn_fp32": bench_attn_fp32, "align": bench_align, "gn": bench_gn}[a.what](a)
+    {"attn": bench_attn, "attn_fp32": bench_attn_fp32, "align": bench_align, "gn": bench_gn, "upconv": bench_upconv}[a.what](a)
