@@ -11,6 +11,7 @@
 //           16-byte vectors, the group statistics are reduced from the partials in the prologue.
 // Algorithmic traffic: 2 reads + 1 write of the activation.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -33,6 +34,8 @@ struct GnParams {
     int chunks, rows_per_chunk;
     float eps;
     int act;               // 0 = none, 1 = SiLU
+    float* stat;           // [N][G][2] mean, rstd (written by gn_finalize_kernel; staged kernels only)
+    int stages;            // ring depth of the staged kernels
 };
 
 template <typename T> struct GnVec { static constexpr int N = 16 / sizeof(T); };
@@ -216,6 +219,249 @@ __global__ void __launch_bounds__(kGnMaxThreads, 2) gn_apply_kernel(const GnPara
     for (; row < row1; row += p.R) {
         const size_t off = (size_t)row * p.C + cv * VN;
         emit(ldg_stream16(xs + off), off);
+    }
+}
+
+// =============================================================================================
+// Staged variants (used whenever one CTA covers all channels of a pixel row, i.e. every shape of the SD2 UNet / VAE in 16-bit).
+// The register-held loads above cap the bytes in flight per SM at 64 KB (64-register budget at 1024 resident threads), and
+// every CTA of gn_apply re-reduced all chunk partials behind a barrier.  Here a producer warp streams the CTA's rows -- one
+// contiguous range of the NHWC tensor -- through a shared-memory ring with 1-D bulk copies (TMA engine, completion on
+// mbarriers, no registers held by loads in flight: ring depth x 32 KB per CTA), the consumer warps read each stage with
+// conflict-free 16-byte shared loads, and the group statistics are finalised ONCE per (sample, group) by gn_finalize_kernel.
+// Same arithmetic and the same fixed summation orders per thread as above => still bit-reproducible.
+// =============================================================================================
+constexpr int kGnU = 4;                 // 16-byte vectors per consumer thread per stage
+constexpr int kGnMaxStages = 6;
+constexpr int kGnStreamThreads = kGnMaxThreads + 32;
+
+__device__ __forceinline__ uint32_t gn_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void gn_bar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gn_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void gn_bar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    int spins = 0;
+    do {
+        asm volatile("{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], %2, 100000;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                     : "=r"(ok) : "r"(gn_smem_u32(bar)), "r"(parity) : "memory");
+        if (!ok && ++spins > 4000000) __trap();          // a lost copy must not hang the device
+    } while (!ok);
+}
+__device__ __forceinline__ void gn_bar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gn_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void gn_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gn_smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(gn_smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(gn_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void gn_consumer_sync(int nthreads) {      // named barrier 1: the consumer warps only
+    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+
+// mean / rstd of every (sample, group) from the per-chunk partials; one CTA per sample, 8 lanes per group.
+__global__ void __launch_bounds__(512) gn_finalize_kernel(const GnParams p) {
+    const int n = blockIdx.x;
+    const int g = threadIdx.x >> 3, part = threadIdx.x & 7;
+    double a = 0.0, b = 0.0;
+    if (g < p.G) {
+        const double* src = p.partial + ((size_t)n * p.chunks * p.G + g) * 2;
+        for (int c = part; c < p.chunks; c += 8) { a += src[(size_t)c * p.G * 2]; b += src[(size_t)c * p.G * 2 + 1]; }
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {                 // fixed tree over the 8 lanes of a group
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (g < p.G && part == 0) {
+        const double cnt = (double)p.HW * (double)p.cpg;
+        const double mean = a / cnt;
+        double var = b / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        p.stat[((size_t)n * p.G + g) * 2] = (float)mean;
+        p.stat[((size_t)n * p.G + g) * 2 + 1] = rsqrtf((float)var + p.eps);
+    }
+}
+
+template <typename T, bool APPLY, bool HAS_PRE>
+__global__ void __launch_bounds__(kGnStreamThreads, 2) gn_staged_kernel(const GnParams p) {
+    constexpr int VN = GnVec<T>::N;
+    extern __shared__ __align__(128) unsigned char gsm[];
+    __shared__ __align__(8) uint64_t full_bar[kGnMaxStages], empty_bar[kGnMaxStages];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ncons = p.CV * p.R;                       // consumer threads: thread (r, cv) = one 16-byte column of row r
+    const int ncw = (ncons + 31) >> 5;                  // consumer warps; warp ncw is the producer
+    const int n = blockIdx.y, chunk = blockIdx.x;
+    const int row0 = chunk * p.rows_per_chunk;
+    const int nrows = min(p.HW, row0 + p.rows_per_chunk) - row0;
+    const int rows_stage = p.R * kGnU;
+    const int nstage = (nrows + rows_stage - 1) / rows_stage;
+    const size_t row_bytes = (size_t)p.C * sizeof(T);
+    const uint32_t stage_bytes = (uint32_t)(rows_stage * row_bytes);       // = ncons * kGnU * 16
+    const size_t base = ((size_t)n * p.HW + row0) * p.C;                      // element offset of the CTA's first row
+
+    if (tid == 0) {
+        for (int s = 0; s < p.stages; ++s) { gn_bar_init(&full_bar[s], 1); gn_bar_init(&empty_bar[s], (uint32_t)ncw); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == ncw) {
+        // ------------------------------------------------------------------ producer: one lane feeds the ring
+        if (lane == 0) {
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(reinterpret_cast<const T*>(p.x) + base);
+            for (int it = 0; it < nstage; ++it) {
+                const int s = it % p.stages;
+                if (it >= p.stages) gn_bar_wait(&empty_bar[s], ((it / p.stages) - 1) & 1);
+                const int r_begin = it * rows_stage;
+                const uint32_t bytes = (uint32_t)(min(rows_stage, nrows - r_begin) * row_bytes);
+                gn_bulk_g2s(gsm + (size_t)s * stage_bytes, src + (size_t)r_begin * row_bytes, bytes, &full_bar[s]);
+            }
+        }
+        return;
+    }
+    if (warp > ncw) return;
+
+    // ---------------------------------------------------------------------- consumers
+    const bool active = tid < ncons;
+    const int cv = active ? tid % p.CV : 0, r = active ? tid / p.CV : 0;
+    const int csync = ncw * 32;
+    unsigned char* after_ring = gsm + (size_t)p.stages * stage_bytes;
+    float pre[VN];
+#pragma unroll
+    for (int i = 0; i < VN; ++i) pre[i] = 0.f;
+    if (HAS_PRE && active) gn_unpack<T>(*reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.pre) + (size_t)n * p.C + cv * VN), pre);
+
+    if constexpr (APPLY) {
+        float* sa = reinterpret_cast<float*>(after_ring);
+        float* sb = sa + p.C;
+        for (int c = tid; c < p.C; c += csync) {
+            const int g = c / p.cpg;
+            const float2 st = __ldg(reinterpret_cast<const float2*>(p.stat) + (size_t)n * p.G + g);
+            const float gam = p.gamma ? Cvt<T>::to_f(reinterpret_cast<const T*>(p.gamma)[c]) : 1.f;
+            const float bet = p.beta ? Cvt<T>::to_f(reinterpret_cast<const T*>(p.beta)[c]) : 0.f;
+            const float a = st.y * gam;
+            sa[c] = a;
+            sb[c] = fmaf(-a, st.x, bet);
+        }
+        gn_consumer_sync(csync);
+        float a[VN], b[VN];
+#pragma unroll
+        for (int i = 0; i < VN; ++i) { a[i] = sa[cv * VN + i]; b[i] = sb[cv * VN + i]; }
+        T* ys = reinterpret_cast<T*>(p.y) + base;
+        const int act = p.act;
+        for (int it = 0; it < nstage; ++it) {
+            const int s = it % p.stages;
+            gn_bar_wait(&full_bar[s], (it / p.stages) & 1);
+            const uint4* st = reinterpret_cast<const uint4*>(gsm + (size_t)s * stage_bytes);
+            const int r_begin = it * rows_stage;
+            uint4 in[kGnU];
+#pragma unroll
+            for (int u = 0; u < kGnU; ++u)
+                if (active && r_begin + u * p.R + r < nrows) in[u] = st[u * ncons + tid];
+            __syncwarp();
+            if (lane == 0) gn_bar_arrive(&empty_bar[s]);
+#pragma unroll
+            for (int u = 0; u < kGnU; ++u) {
+                const int row = r_begin + u * p.R + r;
+                if (active && row < nrows) {
+                    float f[VN];
+                    gn_unpack<T>(in[u], f);
+                    alignas(16) T o[VN];
+#pragma unroll
+                    for (int i = 0; i < VN; ++i) {
+                        const float xin = HAS_PRE ? Cvt<T>::round(f[i] + pre[i]) : f[i];
+                        float v = Cvt<T>::round(fmaf(xin, a[i], b[i]));        // group_norm output, rounded to T like torch
+                        if (act == 1) v = __fdividef(v, 1.f + __expf(-v));      // SiLU on the rounded value
+                        o[i] = Cvt<T>::from_f(v);
+                    }
+                    *reinterpret_cast<uint4*>(ys + (size_t)row * p.C + cv * VN) = *reinterpret_cast<const uint4*>(o);
+                }
+            }
+        }
+    } else {
+        float shift[VN], s1[VN], s2[VN];
+        if (active) {
+            gn_unpack<T>(*reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.x) + (size_t)n * p.HW * p.C + cv * VN), shift);
+#pragma unroll
+            for (int i = 0; i < VN; ++i) { shift[i] = HAS_PRE ? Cvt<T>::round(shift[i] + pre[i]) : shift[i]; s1[i] = 0.f; s2[i] = 0.f; }
+        }
+        for (int it = 0; it < nstage; ++it) {
+            const int s = it % p.stages;
+            gn_bar_wait(&full_bar[s], (it / p.stages) & 1);
+            const uint4* st = reinterpret_cast<const uint4*>(gsm + (size_t)s * stage_bytes);
+            const int r_begin = it * rows_stage;
+            uint4 in[kGnU];
+#pragma unroll
+            for (int u = 0; u < kGnU; ++u)
+                if (active && r_begin + u * p.R + r < nrows) in[u] = st[u * ncons + tid];
+            __syncwarp();
+            if (lane == 0) gn_bar_arrive(&empty_bar[s]);
+#pragma unroll
+            for (int u = 0; u < kGnU; ++u) {
+                if (active && r_begin + u * p.R + r < nrows) {
+                    float f[VN];
+                    gn_unpack<T>(in[u], f);
+#pragma unroll
+                    for (int i = 0; i < VN; ++i) {
+                        const float d = (HAS_PRE ? Cvt<T>::round(f[i] + pre[i]) : f[i]) - shift[i];
+                        s1[i] += d;
+                        s2[i] = fmaf(d, d, s2[i]);
+                    }
+                }
+            }
+        }
+        // every consumer has read its last stage: the ring is free and holds the parked sums from here on
+        gn_consumer_sync(csync);
+        float* st1 = reinterpret_cast<float*>(gsm);                    // [R][C] shifted sums per row-thread
+        float* st2 = st1 + (size_t)p.R * p.C;                         // [R][C] shifted sums of squares
+        float* stK = st2 + (size_t)p.R * p.C;                         // [C]    the shift of each channel
+        double* seg = reinterpret_cast<double*>(stK + p.C);            // [Q][C][2] partial channel sums of the row segments
+        if (active) {
+            float* d1 = st1 + (size_t)r * p.C + cv * VN;
+            float* d2 = st2 + (size_t)r * p.C + cv * VN;
+#pragma unroll
+            for (int i = 0; i < VN; i += 4) {
+                *reinterpret_cast<float4*>(d1 + i) = make_float4(s1[i], s1[i + 1], s1[i + 2], s1[i + 3]);
+                *reinterpret_cast<float4*>(d2 + i) = make_float4(s2[i], s2[i + 1], s2[i + 2], s2[i + 3]);
+            }
+            if (r == 0) {
+#pragma unroll
+                for (int i = 0; i < VN; ++i) stK[cv * VN + i] = shift[i];
+            }
+        }
+        gn_consumer_sync(csync);
+        // un-shift in double; the R row-threads of a channel are combined in Q fixed segments, then the segments in order
+        int Q = ncons / p.C;
+        if (Q < 1) Q = 1;
+        if (Q > p.R) Q = p.R;
+        const int seg_rows = (p.R + Q - 1) / Q;
+        for (int idx = tid; idx < Q * p.C; idx += csync) {
+            const int q = idx / p.C, c = idx - q * p.C;
+            const double K = (double)stK[c];
+            double a = 0.0, b = 0.0;
+            const int rr1 = min(p.R, (q + 1) * seg_rows);
+            for (int rr = q * seg_rows; rr < rr1; ++rr) {
+                const double nn = rr < nrows ? (double)((nrows - rr + p.R - 1) / p.R) : 0.0;
+                const double d1 = (double)st1[(size_t)rr * p.C + c], d2 = (double)st2[(size_t)rr * p.C + c];
+                a += d1 + nn * K;
+                b += d2 + 2.0 * K * d1 + nn * K * K;
+            }
+            seg[(size_t)idx * 2] = a;
+            seg[(size_t)idx * 2 + 1] = b;
+        }
+        gn_consumer_sync(csync);
+        // channels -> groups (fixed order)
+        for (int g = tid; g < p.G; g += csync) {
+            double a = 0.0, b = 0.0;
+            for (int c = g * p.cpg; c < (g + 1) * p.cpg; ++c)
+                for (int q = 0; q < Q; ++q) { a += seg[((size_t)q * p.C + c) * 2]; b += seg[((size_t)q * p.C + c) * 2 + 1]; }
+            double* out = p.partial + (((size_t)n * p.chunks + chunk) * p.G + g) * 2;
+            out[0] = a;
+            out[1] = b;
+        }
     }
 }
 
@@ -540,6 +786,38 @@ static int gn_plan(GnParams& p, int es) {
     return 0;
 }
 
+// RD_GN_STAGED=0 keeps the register-staged kernels everywhere (A/B measurements); RD_GN_STAGES = ring depth (2..6, default 3:
+// two CTAs of 3 x 32 KB per SM; 4 and 6 = one CTA per SM were measured 15-25 % slower)
+// Staged kernels: when one CTA covers all channels of a pixel row and a sample is at least kGnStagedMinBytes.  Measured on the
+// preset's shapes (profiles/r2_gn_staged.txt): +10...17 % on the three large VAE-decoder levels (21-85 MB per sample), even at
+// 3-7 MB, 7-25 % slower below (few rows per CTA: the ring never fills, and the finalise launch is a third of the time).
+// RD_GN_STAGED=2 forces them for every eligible shape (tests).
+constexpr long long kGnStagedMinBytes = 16ll << 20;
+static int g_gn_mode_forced = -1;          // rd_groupnorm_set_staged
+static bool gn_use_staged(const GnParams& p, int es) {
+    static const int env_mode = [] { const char* e = getenv("RD_GN_STAGED"); return e ? atoi(e) : 1; }();
+    const int mode = g_gn_mode_forced >= 0 ? g_gn_mode_forced : env_mode;
+    if (mode == 0 || p.Cs != p.C) return false;
+    return mode == 2 || (long long)p.HW * p.C * es >= kGnStagedMinBytes;
+}
+static int gn_stage_count() {
+    static const int n = [] {
+        const char* e = getenv("RD_GN_STAGES");
+        int v = e ? atoi(e) : 3;
+        return v < 2 ? 2 : (v > kGnMaxStages ? kGnMaxStages : v);
+    }();
+    return n;
+}
+
+template <typename T>
+static void gn_launch_staged(const GnParams& p, dim3 grid, int nthr, size_t sm, cudaStream_t st) {
+    if (p.pre) gn_staged_kernel<T, false, true><<<grid, nthr, sm, st>>>(p);
+    else       gn_staged_kernel<T, false, false><<<grid, nthr, sm, st>>>(p);
+    gn_finalize_kernel<<<p.N, 512, 0, st>>>(p);
+    if (p.pre) gn_staged_kernel<T, true, true><<<grid, nthr, sm, st>>>(p);
+    else       gn_staged_kernel<T, true, false><<<grid, nthr, sm, st>>>(p);
+}
+
 }  // namespace rd
 
 using namespace rd;
@@ -547,7 +825,23 @@ using namespace rd;
 extern "C" {
 
 int64_t rd_groupnorm_workspace_bytes(int N, int G) {
-    return (int64_t)N * kGnMaxChunks * (G > 0 ? G : 1) * 2 * (int64_t)sizeof(double);
+    const int64_t g = G > 0 ? G : 1;
+    return (int64_t)N * kGnMaxChunks * g * 2 * (int64_t)sizeof(double) + (int64_t)N * g * 2 * (int64_t)sizeof(float);
+}
+
+int rd_groupnorm_set_staged(int mode) {
+    RD_CHECK_ARG(mode >= -1 && mode <= 2, "mode must be -1 (default), 0 (register-staged), 1 (by size) or 2 (staged whenever eligible)");
+    g_gn_mode_forced = mode;
+    return RD_OK;
+}
+
+int rd_groupnorm_launch_count(int HW, int C, int G, rd_dtype dtype) {
+    if (HW < 1 || C < 1 || G < 1 || G > 64 || C % G != 0 || !(dtype == RD_F32 || dtype == RD_F16 || dtype == RD_BF16)) return 0;
+    GnParams p{};
+    p.C = C; p.G = G; p.cpg = C / G; p.HW = HW;
+    const int es = dtype == RD_F32 ? 4 : 2;
+    if (C % (16 / es) != 0 || gn_plan(p, es) != 0) return 0;
+    return gn_use_staged(p, es) ? 3 : 2;
 }
 
 int rd_groupnorm_nhwc(const void* x, void* y, const void* gamma, const void* beta, const void* pre_add, int N, int HW,
@@ -567,13 +861,47 @@ int rd_groupnorm_nhwc(const void* x, void* y, const void* gamma, const void* bet
     p.partial = reinterpret_cast<double*>(workspace);
     p.N = N; p.HW = HW; p.C = C; p.G = G; p.cpg = C / G; p.eps = eps; p.act = act;
     if (gn_plan(p, es) != 0) { set_error("no channel slicing found for C=%d G=%d", C, G); return RD_ERR_UNSUPPORTED; }
-    if (workspace_bytes < (int64_t)N * p.chunks * G * 2 * (int64_t)sizeof(double)) {
+    if (workspace_bytes < rd_groupnorm_workspace_bytes(N, G)) {
         set_error("group-norm workspace too small");
         return RD_ERR_WORKSPACE;
     }
     cudaStream_t st = (cudaStream_t)stream;
     const int threads = p.CV * p.R;
     dim3 grid(p.chunks, N, C / p.Cs);
+    if (gn_use_staged(p, es)) {
+        // staged kernels: the CTA's rows are one contiguous range, streamed through a shared-memory ring by bulk copies
+        const size_t stage_bytes = (size_t)threads * kGnU * 16;
+        p.stages = gn_stage_count();
+        p.stat = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(workspace) + (size_t)N * kGnMaxChunks * G * 2 * sizeof(double));
+        const size_t ring = p.stages * stage_bytes;
+        const size_t park = ((2 * (size_t)p.R + 1) * C) * sizeof(float) + (size_t)threads * 2 * sizeof(double);
+        if (park > ring) { set_error("group-norm ring smaller than the reduction scratch"); return RD_ERR_UNSUPPORTED; }
+        const size_t sm = ring + 2 * (size_t)C * sizeof(float);
+        {
+            static PerDeviceOnce configured;
+            if (configured.needed()) {
+                const int lim = 200 * 1024;
+                const void* fns[] = {
+                    (const void*)gn_staged_kernel<float, false, false>, (const void*)gn_staged_kernel<float, false, true>,
+                    (const void*)gn_staged_kernel<float, true, false>, (const void*)gn_staged_kernel<float, true, true>,
+                    (const void*)gn_staged_kernel<__half, false, false>, (const void*)gn_staged_kernel<__half, false, true>,
+                    (const void*)gn_staged_kernel<__half, true, false>, (const void*)gn_staged_kernel<__half, true, true>,
+                    (const void*)gn_staged_kernel<__nv_bfloat16, false, false>, (const void*)gn_staged_kernel<__nv_bfloat16, false, true>,
+                    (const void*)gn_staged_kernel<__nv_bfloat16, true, false>, (const void*)gn_staged_kernel<__nv_bfloat16, true, true>};
+                for (const void* f : fns) RD_CUDA(cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, lim));
+                configured.done();
+            }
+        }
+        const int nthr = ((threads + 31) / 32 + 1) * 32;          // consumer warps + the producer warp
+        dim3 g2(p.chunks, N);
+        switch (dtype) {
+            case RD_F32: gn_launch_staged<float>(p, g2, nthr, sm, st); break;
+            case RD_F16: gn_launch_staged<__half>(p, g2, nthr, sm, st); break;
+            default:     gn_launch_staged<__nv_bfloat16>(p, g2, nthr, sm, st); break;
+        }
+        RD_LAUNCH_CHECK("gn staged kernels");
+        return RD_OK;
+    }
     // (a cp.async staging ring holding eight 16-byte loads per thread in shared memory instead of four in registers was
     //  measured 3-6 % SLOWER on the three decoder sizes -- tools/probes, profiles/r2_gn_variants.txt -- and is not kept)
     const size_t sm_stats = 2 * (size_t)p.Cs * sizeof(double) + (2 * (size_t)p.R + 1) * p.Cs * sizeof(float);

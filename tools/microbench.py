@@ -184,15 +184,26 @@ def bench_gn(args):
     from rollingdepth_b200 import ops
     dev = torch.device("cuda:0")
     hbm, _, src = peaks()
-    for name, N, H, W, Cc in [("dec L3 12x432x768x128", 12, 432, 768, 128), ("dec L2 12x216x384x256", 12, 216, 384, 256),
-                              ("dec L1 12x108x192x512", 12, 108, 192, 512)]:
+    cases = [("dec L3 12x432x768x128", 12, 432, 768, 128), ("dec L2 12x216x384x256", 12, 216, 384, 256),
+             ("dec L1 12x108x192x512", 12, 108, 192, 512)]
+    if args.full:       # UNet activations of one 16-snippet batch (48 frames) and the small decoder levels
+        cases += [("unet L0 48x54x96x320", 48, 54, 96, 320), ("unet L0 cat 48x54x96x640", 48, 54, 96, 640),
+                  ("unet L1 48x27x48x640", 48, 27, 48, 640), ("unet L1 cat 48x27x48x1280", 48, 27, 48, 1280),
+                  ("unet L2 48x14x24x1280", 48, 14, 24, 1280), ("unet L3 cat 48x7x12x2560", 48, 7, 12, 2560),
+                  ("dec L0 12x54x96x512", 12, 54, 96, 512)]
+    for name, N, H, W, Cc in cases:
         x = torch.randn(N, Cc, H, W, device=dev, dtype=torch.float16).contiguous(memory_format=torch.channels_last)
         res = torch.randn_like(x)
         w = torch.ones(Cc, device=dev, dtype=torch.float16)
         b = torch.zeros(Cc, device=dev, dtype=torch.float16)
         nbytes = x.numel() * 2
+        if args.only and args.only not in name:
+            continue
         med, best = time_cuda(lambda: ops.group_norm_nhwc(x, 32, w, b, 1e-6, True))
         print(json.dumps(dict(bench="groupnorm+silu", case=name, ms=med, algorithmic_GB=3 * nbytes / 1e9,
+                              GBs=3 * nbytes / med / 1e6, frac_of_hbm=3 * nbytes / med / 1e6 / hbm, peak_src=src)), flush=True)
+        med, best = time_cuda(lambda: ops.group_norm_nhwc(x, 32, w, b, 1e-6, False))
+        print(json.dumps(dict(bench="groupnorm (no SiLU)", case=name, ms=med, algorithmic_GB=3 * nbytes / 1e9,
                               GBs=3 * nbytes / med / 1e6, frac_of_hbm=3 * nbytes / med / 1e6 / hbm, peak_src=src)), flush=True)
         med, best = time_cuda(lambda: ops.bias_residual_nhwc(x, bias=b, residual=res, inplace=False))
         print(json.dumps(dict(bench="bias+residual", case=name, ms=med, algorithmic_GB=3 * nbytes / 1e9,
