@@ -51,6 +51,131 @@ __device__ __forceinline__ void gn_unpack(const uint4& u, float* f) {
     }
 }
 
+// ---- packed fp32x2 element math (sm_100: FFMA2 / FADD2 / FMUL2 do two lanes in one issue slot).  These kernels are not only
+// bandwidth- but also energy-limited inside a step (the step runs at the board's power cap): the pair forms below do the same
+// fp32 arithmetic with the same roundings as the scalar code they replace in ~7 instead of ~12.5 issue slots per element
+// (no range fix-up around ex2: 1 + ex2(t) is 1 for every t the fix-up would have touched; v * rcp(d) instead of div.approx).
+__device__ __forceinline__ uint64_t gn_pk(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 gn_upk(uint64_t v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+__device__ __forceinline__ uint64_t gn_ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t gn_fadd2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t gn_fmul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float gn_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float gn_rcp(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// two adjacent elements of T <-> one packed fp32 pair (one conversion instruction per pair when packing)
+template <typename T> struct GnPair;
+template <> struct GnPair<__half> {
+    static __device__ __forceinline__ uint64_t unpack(uint32_t w) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w));
+        return gn_pk(f.x, f.y);
+    }
+    static __device__ __forceinline__ uint32_t pack(uint64_t v) {
+        const float2 f = gn_upk(v);
+        const __half2 h = __floats2half2_rn(f.x, f.y);
+        return *reinterpret_cast<const uint32_t*>(&h);
+    }
+};
+template <> struct GnPair<__nv_bfloat16> {
+    static __device__ __forceinline__ uint64_t unpack(uint32_t w) {
+        return gn_pk(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+    }
+    static __device__ __forceinline__ uint32_t pack(uint64_t v) {
+        const float2 f = gn_upk(v);
+        const __nv_bfloat162 h = __floats2bfloat162_rn(f.x, f.y);
+        return *reinterpret_cast<const uint32_t*>(&h);
+    }
+};
+// SiLU of a pair: v / (1 + exp(-v)) as v * rcp(1 + ex2(-v * log2 e))
+__device__ __forceinline__ uint64_t gn_silu2(uint64_t v) {
+    const float2 t = gn_upk(gn_fmul2(v, gn_pk(-1.4426950408889634f, -1.4426950408889634f)));
+    const float2 d = gn_upk(gn_fadd2(gn_pk(gn_ex2(t.x), gn_ex2(t.y)), gn_pk(1.f, 1.f)));
+    return gn_fmul2(v, gn_pk(gn_rcp(d.x), gn_rcp(d.y)));
+}
+
+// One 16-byte vector of the normalise(+SiLU) pass: y = act(round_T(round_T(x + pre) * a + b)); a2 / b2 / pre2 hold the per-channel
+// constants of the vector's VN channels as VN / 2 packed pairs.
+template <typename T, bool HAS_PRE>
+__device__ __forceinline__ uint4 gn_apply_vec(const uint4& in, const uint64_t* a2, const uint64_t* b2, const uint64_t* pre2, int act) {
+    const uint32_t w[4] = {in.x, in.y, in.z, in.w};
+    uint32_t o[4];
+    if constexpr (sizeof(T) == 2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint64_t x = GnPair<T>::unpack(w[j]);
+            if (HAS_PRE) x = GnPair<T>::unpack(GnPair<T>::pack(gn_fadd2(x, pre2[j])));
+            uint32_t h = GnPair<T>::pack(gn_ffma2(x, a2[j], b2[j]));          // group_norm output, rounded to T like torch
+            if (act == 1) h = GnPair<T>::pack(gn_silu2(GnPair<T>::unpack(h)));  // SiLU on the rounded value
+            o[j] = h;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            uint64_t x = gn_pk(__uint_as_float(w[2 * j]), __uint_as_float(w[2 * j + 1]));
+            if (HAS_PRE) x = gn_fadd2(x, pre2[j]);
+            uint64_t y = gn_ffma2(x, a2[j], b2[j]);
+            if (act == 1) y = gn_silu2(y);
+            const float2 f = gn_upk(y);
+            o[2 * j] = __float_as_uint(f.x);
+            o[2 * j + 1] = __float_as_uint(f.y);
+        }
+    }
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// One 16-byte vector of the statistics pass: d = round_T(x + pre) - shift; s1 += d; s2 += d * d (per channel, packed pairs);
+// nshift2 holds -shift.
+template <typename T, bool HAS_PRE>
+__device__ __forceinline__ void gn_stats_vec(const uint4& in, const uint64_t* nshift2, const uint64_t* pre2, uint64_t* s1, uint64_t* s2) {
+    const uint32_t w[4] = {in.x, in.y, in.z, in.w};
+    if constexpr (sizeof(T) == 2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint64_t x = GnPair<T>::unpack(w[j]);
+            if (HAS_PRE) x = GnPair<T>::unpack(GnPair<T>::pack(gn_fadd2(x, pre2[j])));
+            const uint64_t d = gn_fadd2(x, nshift2[j]);
+            s1[j] = gn_fadd2(s1[j], d);
+            s2[j] = gn_ffma2(d, d, s2[j]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            uint64_t x = gn_pk(__uint_as_float(w[2 * j]), __uint_as_float(w[2 * j + 1]));
+            if (HAS_PRE) x = gn_fadd2(x, pre2[j]);
+            const uint64_t d = gn_fadd2(x, nshift2[j]);
+            s1[j] = gn_fadd2(s1[j], d);
+            s2[j] = gn_ffma2(d, d, s2[j]);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(kGnMaxThreads, 2) gn_stats_kernel(const GnParams p) {
@@ -69,14 +194,22 @@ __global__ void __launch_bounds__(kGnMaxThreads, 2) gn_stats_kernel(const GnPara
     const int row0 = chunk * p.rows_per_chunk;
     const int row1 = min(p.HW, row0 + p.rows_per_chunk);
 
-    float shift[VN], s1[VN], s2[VN], pre[VN];
     if (active) {
+        constexpr int NP = VN / 2;
+        float shift[VN], pre[VN];
 #pragma unroll
         for (int i = 0; i < VN; ++i) pre[i] = 0.f;
-        if (p.pre) gn_unpack<T>(*reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.pre) + (size_t)n * p.C + c_off + cv * VN), pre);
+        const bool has_pre = p.pre != nullptr;
+        if (has_pre) gn_unpack<T>(*reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.pre) + (size_t)n * p.C + c_off + cv * VN), pre);
         gn_unpack<T>(*reinterpret_cast<const uint4*>(xs + (size_t)cv * VN), shift);   // pixel 0 of the sample
+        uint64_t nshift2[NP], pre2[NP], s1[NP], s2[NP];
 #pragma unroll
-        for (int i = 0; i < VN; ++i) { shift[i] = Cvt<T>::round(shift[i] + pre[i]); s1[i] = 0.f; s2[i] = 0.f; }
+        for (int j = 0; j < NP; ++j) {
+            nshift2[j] = gn_pk(-Cvt<T>::round(shift[2 * j] + pre[2 * j]), -Cvt<T>::round(shift[2 * j + 1] + pre[2 * j + 1]));
+            pre2[j] = gn_pk(pre[2 * j], pre[2 * j + 1]);
+            s1[j] = 0ull;
+            s2[j] = 0ull;
+        }
         int row = row0 + r;
         // four independent 16-byte loads in flight per thread
         for (; row + 3 * p.R < row1; row += 4 * p.R) {
@@ -84,39 +217,32 @@ __global__ void __launch_bounds__(kGnMaxThreads, 2) gn_stats_kernel(const GnPara
 #pragma unroll
             for (int u = 0; u < 4; ++u) in[u] = ldg_stream16(xs + (size_t)(row + u * p.R) * p.C + cv * VN);
 #pragma unroll
-            for (int u = 0; u < 4; u += 2) {
-                float fa[VN], fb[VN];
-                gn_unpack<T>(in[u], fa);
-                gn_unpack<T>(in[u + 1], fb);
-#pragma unroll
-                for (int i = 0; i < VN; ++i) {
-                    const float da = Cvt<T>::round(fa[i] + pre[i]) - shift[i], db = Cvt<T>::round(fb[i] + pre[i]) - shift[i];
-                    s1[i] += da + db;
-                    s2[i] = fmaf(da, da, fmaf(db, db, s2[i]));
-                }
+            for (int u = 0; u < 4; ++u) {
+                if (has_pre) gn_stats_vec<T, true>(in[u], nshift2, pre2, s1, s2);
+                else         gn_stats_vec<T, false>(in[u], nshift2, pre2, s1, s2);
             }
         }
         for (; row < row1; row += p.R) {
-            float fa[VN];
-            gn_unpack<T>(ldg_stream16(xs + (size_t)row * p.C + cv * VN), fa);
-#pragma unroll
-            for (int i = 0; i < VN; ++i) {
-                const float da = Cvt<T>::round(fa[i] + pre[i]) - shift[i];
-                s1[i] += da;
-                s2[i] = fmaf(da, da, s2[i]);
-            }
+            const uint4 in = ldg_stream16(xs + (size_t)row * p.C + cv * VN);
+            if (has_pre) gn_stats_vec<T, true>(in, nshift2, pre2, s1, s2);
+            else         gn_stats_vec<T, false>(in, nshift2, pre2, s1, s2);
         }
         // park the per-thread shifted sums; the row-threads of a channel are combined below in the order r = 0..R-1
         float* d1 = st1 + (size_t)r * p.Cs + cv * VN;
         float* d2 = st2 + (size_t)r * p.Cs + cv * VN;
 #pragma unroll
-        for (int i = 0; i < VN; i += 4) {
-            *reinterpret_cast<float4*>(d1 + i) = make_float4(s1[i], s1[i + 1], s1[i + 2], s1[i + 3]);
-            *reinterpret_cast<float4*>(d2 + i) = make_float4(s2[i], s2[i + 1], s2[i + 2], s2[i + 3]);
+        for (int j = 0; j < NP; j += 2) {
+            const float2 a0 = gn_upk(s1[j]), a1 = gn_upk(s1[j + 1]), b0 = gn_upk(s2[j]), b1 = gn_upk(s2[j + 1]);
+            *reinterpret_cast<float4*>(d1 + 2 * j) = make_float4(a0.x, a0.y, a1.x, a1.y);
+            *reinterpret_cast<float4*>(d2 + 2 * j) = make_float4(b0.x, b0.y, b1.x, b1.y);
         }
         if (r == 0) {
 #pragma unroll
-            for (int i = 0; i < VN; ++i) stK[cv * VN + i] = shift[i];
+            for (int j = 0; j < NP; ++j) {
+                const float2 k = gn_upk(nshift2[j]);
+                stK[cv * VN + 2 * j] = -k.x;
+                stK[cv * VN + 2 * j + 1] = -k.y;
+            }
         }
     }
     __syncthreads();
@@ -181,26 +307,27 @@ __global__ void __launch_bounds__(kGnMaxThreads, 2) gn_apply_kernel(const GnPara
 
     const int cv = threadIdx.x % p.CV, r = threadIdx.x / p.CV;
     if (r >= p.R) return;
-    float a[VN], b[VN], pre[VN];
+    constexpr int NP = VN / 2;
+    float pre[VN];
 #pragma unroll
-    for (int i = 0; i < VN; ++i) { a[i] = sa[cv * VN + i]; b[i] = sb[cv * VN + i]; pre[i] = 0.f; }
-    if (p.pre) gn_unpack<T>(*reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.pre) + (size_t)n * p.C + c_off + cv * VN), pre);
+    for (int i = 0; i < VN; ++i) pre[i] = 0.f;
+    const bool has_pre = p.pre != nullptr;
+    if (has_pre) gn_unpack<T>(*reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.pre) + (size_t)n * p.C + c_off + cv * VN), pre);
+    uint64_t a2[NP], b2[NP], pre2[NP];
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+        a2[j] = gn_pk(sa[cv * VN + 2 * j], sa[cv * VN + 2 * j + 1]);
+        b2[j] = gn_pk(sb[cv * VN + 2 * j], sb[cv * VN + 2 * j + 1]);
+        pre2[j] = gn_pk(pre[2 * j], pre[2 * j + 1]);
+    }
     const T* xs = reinterpret_cast<const T*>(p.x) + (size_t)n * p.HW * p.C + c_off;
     T* ys = reinterpret_cast<T*>(p.y) + (size_t)n * p.HW * p.C + c_off;
     const int row0 = chunk * p.rows_per_chunk;
     const int row1 = min(p.HW, row0 + p.rows_per_chunk);
+    const int act = p.act;
     auto emit = [&](const uint4& in, size_t off) {
-        float f[VN];
-        gn_unpack<T>(in, f);
-        alignas(16) T o[VN];
-#pragma unroll
-        for (int i = 0; i < VN; ++i) {
-            const float xin = p.pre ? Cvt<T>::round(f[i] + pre[i]) : f[i];
-            float v = Cvt<T>::round(fmaf(xin, a[i], b[i]));        // group_norm output, rounded to T like torch
-            if (p.act == 1) v = __fdividef(v, 1.f + __expf(-v));    // SiLU on the rounded value
-            o[i] = Cvt<T>::from_f(v);
-        }
-        *reinterpret_cast<uint4*>(ys + off) = *reinterpret_cast<const uint4*>(o);
+        *reinterpret_cast<uint4*>(ys + off) = has_pre ? gn_apply_vec<T, true>(in, a2, b2, pre2, act)
+                                                      : gn_apply_vec<T, false>(in, a2, b2, pre2, act);
     };
     int row = row0 + r;
     // four independent 16-byte loads in flight per thread: with one, the 64 resident warps of an SM keep only 32 KB
@@ -347,9 +474,14 @@ __global__ void __launch_bounds__(kGnStreamThreads, 2) gn_staged_kernel(const Gn
             sb[c] = fmaf(-a, st.x, bet);
         }
         gn_consumer_sync(csync);
-        float a[VN], b[VN];
+        constexpr int NP = VN / 2;
+        uint64_t a2[NP], b2[NP], pre2[NP];
 #pragma unroll
-        for (int i = 0; i < VN; ++i) { a[i] = sa[cv * VN + i]; b[i] = sb[cv * VN + i]; }
+        for (int j = 0; j < NP; ++j) {
+            a2[j] = gn_pk(sa[cv * VN + 2 * j], sa[cv * VN + 2 * j + 1]);
+            b2[j] = gn_pk(sb[cv * VN + 2 * j], sb[cv * VN + 2 * j + 1]);
+            pre2[j] = gn_pk(pre[2 * j], pre[2 * j + 1]);
+        }
         T* ys = reinterpret_cast<T*>(p.y) + base;
         const int act = p.act;
         for (int it = 0; it < nstage; ++it) {
@@ -366,27 +498,22 @@ __global__ void __launch_bounds__(kGnStreamThreads, 2) gn_staged_kernel(const Gn
 #pragma unroll
             for (int u = 0; u < kGnU; ++u) {
                 const int row = r_begin + u * p.R + r;
-                if (active && row < nrows) {
-                    float f[VN];
-                    gn_unpack<T>(in[u], f);
-                    alignas(16) T o[VN];
-#pragma unroll
-                    for (int i = 0; i < VN; ++i) {
-                        const float xin = HAS_PRE ? Cvt<T>::round(f[i] + pre[i]) : f[i];
-                        float v = Cvt<T>::round(fmaf(xin, a[i], b[i]));        // group_norm output, rounded to T like torch
-                        if (act == 1) v = __fdividef(v, 1.f + __expf(-v));      // SiLU on the rounded value
-                        o[i] = Cvt<T>::from_f(v);
-                    }
-                    *reinterpret_cast<uint4*>(ys + (size_t)row * p.C + cv * VN) = *reinterpret_cast<const uint4*>(o);
-                }
+                if (active && row < nrows)
+                    *reinterpret_cast<uint4*>(ys + (size_t)row * p.C + cv * VN) = gn_apply_vec<T, HAS_PRE>(in[u], a2, b2, pre2, act);
             }
         }
     } else {
-        float shift[VN], s1[VN], s2[VN];
+        constexpr int NP = VN / 2;
+        uint64_t nshift2[NP], pre2[NP], s1[NP], s2[NP];
+#pragma unroll
+        for (int j = 0; j < NP; ++j) { nshift2[j] = 0ull; pre2[j] = gn_pk(pre[2 * j], pre[2 * j + 1]); s1[j] = 0ull; s2[j] = 0ull; }
         if (active) {
+            float shift[VN];
             gn_unpack<T>(*reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(p.x) + (size_t)n * p.HW * p.C + cv * VN), shift);
 #pragma unroll
-            for (int i = 0; i < VN; ++i) { shift[i] = HAS_PRE ? Cvt<T>::round(shift[i] + pre[i]) : shift[i]; s1[i] = 0.f; s2[i] = 0.f; }
+            for (int j = 0; j < NP; ++j)
+                nshift2[j] = gn_pk(-(HAS_PRE ? Cvt<T>::round(shift[2 * j] + pre[2 * j]) : shift[2 * j]),
+                                   -(HAS_PRE ? Cvt<T>::round(shift[2 * j + 1] + pre[2 * j + 1]) : shift[2 * j + 1]));
         }
         for (int it = 0; it < nstage; ++it) {
             const int s = it % p.stages;
@@ -400,18 +527,8 @@ __global__ void __launch_bounds__(kGnStreamThreads, 2) gn_staged_kernel(const Gn
             __syncwarp();
             if (lane == 0) gn_bar_arrive(&empty_bar[s]);
 #pragma unroll
-            for (int u = 0; u < kGnU; ++u) {
-                if (active && r_begin + u * p.R + r < nrows) {
-                    float f[VN];
-                    gn_unpack<T>(in[u], f);
-#pragma unroll
-                    for (int i = 0; i < VN; ++i) {
-                        const float d = (HAS_PRE ? Cvt<T>::round(f[i] + pre[i]) : f[i]) - shift[i];
-                        s1[i] += d;
-                        s2[i] = fmaf(d, d, s2[i]);
-                    }
-                }
-            }
+            for (int u = 0; u < kGnU; ++u)
+                if (active && r_begin + u * p.R + r < nrows) gn_stats_vec<T, HAS_PRE>(in[u], nshift2, pre2, s1, s2);
         }
         // every consumer has read its last stage: the ring is free and holds the parked sums from here on
         gn_consumer_sync(csync);
@@ -423,13 +540,18 @@ __global__ void __launch_bounds__(kGnStreamThreads, 2) gn_staged_kernel(const Gn
             float* d1 = st1 + (size_t)r * p.C + cv * VN;
             float* d2 = st2 + (size_t)r * p.C + cv * VN;
 #pragma unroll
-            for (int i = 0; i < VN; i += 4) {
-                *reinterpret_cast<float4*>(d1 + i) = make_float4(s1[i], s1[i + 1], s1[i + 2], s1[i + 3]);
-                *reinterpret_cast<float4*>(d2 + i) = make_float4(s2[i], s2[i + 1], s2[i + 2], s2[i + 3]);
+            for (int j = 0; j < NP; j += 2) {
+                const float2 a0 = gn_upk(s1[j]), a1 = gn_upk(s1[j + 1]), b0 = gn_upk(s2[j]), b1 = gn_upk(s2[j + 1]);
+                *reinterpret_cast<float4*>(d1 + 2 * j) = make_float4(a0.x, a0.y, a1.x, a1.y);
+                *reinterpret_cast<float4*>(d2 + 2 * j) = make_float4(b0.x, b0.y, b1.x, b1.y);
             }
             if (r == 0) {
 #pragma unroll
-                for (int i = 0; i < VN; ++i) stK[cv * VN + i] = shift[i];
+                for (int j = 0; j < NP; ++j) {
+                    const float2 k = gn_upk(nshift2[j]);
+                    stK[cv * VN + 2 * j] = -k.x;
+                    stK[cv * VN + 2 * j + 1] = -k.y;
+                }
             }
         }
         gn_consumer_sync(csync);
@@ -498,19 +620,32 @@ __global__ void __launch_bounds__(kGnMaxThreads) bias_residual_kernel(const AddP
             for (int i = 0; i < VN; ++i) add[i] += t[i];
         }
         const size_t base = (size_t)n * p.HW * p.C + cv * VN;
+        uint64_t add2[VN / 2];
+#pragma unroll
+        for (int j = 0; j < VN / 2; ++j) add2[j] = gn_pk(add[2 * j], add[2 * j + 1]);
+        const bool has_res = p.res != nullptr;
         auto emit = [&](const uint4& xin, const uint4& rin, size_t off) {
-            float f[VN];
-            gn_unpack<T>(xin, f);
-            if (p.res) {
-                float g[VN];
-                gn_unpack<T>(rin, g);
+            // (x + residual) + (bias + vec) in fp32, one rounding; packed pairs: same adds in half the issue slots
+            const uint32_t xw[4] = {xin.x, xin.y, xin.z, xin.w}, rw[4] = {rin.x, rin.y, rin.z, rin.w};
+            uint32_t o[4];
+            if constexpr (sizeof(T) == 2) {
 #pragma unroll
-                for (int i = 0; i < VN; ++i) f[i] += g[i];
+                for (int j = 0; j < 4; ++j) {
+                    uint64_t f = GnPair<T>::unpack(xw[j]);
+                    if (has_res) f = gn_fadd2(f, GnPair<T>::unpack(rw[j]));
+                    o[j] = GnPair<T>::pack(gn_fadd2(f, add2[j]));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    uint64_t f = gn_pk(__uint_as_float(xw[2 * j]), __uint_as_float(xw[2 * j + 1]));
+                    if (has_res) f = gn_fadd2(f, gn_pk(__uint_as_float(rw[2 * j]), __uint_as_float(rw[2 * j + 1])));
+                    const float2 g = gn_upk(gn_fadd2(f, add2[j]));
+                    o[2 * j] = __float_as_uint(g.x);
+                    o[2 * j + 1] = __float_as_uint(g.y);
+                }
             }
-            alignas(16) T o[VN];
-#pragma unroll
-            for (int i = 0; i < VN; ++i) o[i] = Cvt<T>::from_f(f[i] + add[i]);
-            *reinterpret_cast<uint4*>(reinterpret_cast<T*>(p.y) + off) = *reinterpret_cast<const uint4*>(o);
+            *reinterpret_cast<uint4*>(reinterpret_cast<T*>(p.y) + off) = make_uint4(o[0], o[1], o[2], o[3]);
         };
         int row = row0 + r;
         // four rows per trip: up to eight independent 16-byte loads in flight per thread before the first store

@@ -24,7 +24,18 @@ def count(module, *inputs, **kw):
     def lin_hook(m, inp, out):
         tot["linear"] += 2 * out.numel() * m.in_features
 
+    def up_hook(m, inp, out):
+        # exact-2x Upsample2D runs in sub-pixel form: 16 instead of 36 multiply-adds per source pixel and channel pair
+        if tuple(out.shape[-2:]) == (2 * inp[0].shape[-2], 2 * inp[0].shape[-1]):
+            saved = 2 * out.numel() * m.conv.in_channels * 9 * 20 // 36
+            tot["conv"] -= saved
+            tot["subpixel_saved"] += saved
+
+    from rollingdepth_b200.sd2.layers import Upsample2D
+    tot["subpixel_saved"] = 0
     for m in module.modules():
+        if isinstance(m, Upsample2D):
+            hooks.append(m.register_forward_hook(up_hook))
         if isinstance(m, nn.Conv2d):
             hooks.append(m.register_forward_hook(conv_hook))
         elif isinstance(m, nn.Linear):
@@ -65,13 +76,15 @@ def main():
             hh, ww = (hh + 1) // 2, (ww + 1) // 2
         attn += layers * 4 * (3 * hh * ww) ** 2 * 64 * heads
     n_snip = sum(max(a.frames - 2 * d, 0) for d in a.dilations)
-    print(f"UNet, one 3-frame snippet: {(un['conv'] + un['linear']) / 1e12:.3f} TFLOP conv + linear, {attn / 1e12:.3f} TFLOP "
+    print(f"UNet, one 3-frame snippet: {(un['conv'] + un['linear']) / 1e12:.3f} TFLOP conv + linear "
+          f"({un['subpixel_saved'] / 1e12:.3f} saved by sub-pixel upsampling), {attn / 1e12:.3f} TFLOP "
           f"cross-frame self-attention; x {n_snip} snippets = {n_snip * (un['conv'] + un['linear']) / 1e15:.3f} + "
           f"{n_snip * attn / 1e15:.3f} PFLOP = {n_snip * (un['conv'] + un['linear']) / 1e12 / a.peak * 1e3:.0f} + "
           f"{n_snip * attn / 1e12 / a.peak * 1e3:.0f} ms at {a.peak} TFLOP/s")
     n_dec = 3 * n_snip
     print(f"VAE encoder: {enc['conv'] / 1e12:.3f} TFLOP of convolutions per {a.height}x{a.width} frame")
-    print(f"VAE decoder: {dec['conv'] / 1e12:.3f} TFLOP of convolutions per frame (+{dec['linear'] / 1e9:.1f} GFLOP linear)")
+    print(f"VAE decoder: {dec['conv'] / 1e12:.3f} TFLOP of convolutions per frame (+{dec['linear'] / 1e9:.1f} GFLOP linear; "
+          f"{dec['subpixel_saved'] / 1e12:.3f} TFLOP saved by the sub-pixel form of the three upsampling convolutions)")
     print(f"{a.frames} frames, dilations {a.dilations}: {n_snip} snippets -> {n_dec} decoded frames = "
           f"{n_dec * dec['conv'] / 1e15:.3f} PFLOP = {n_dec * dec['conv'] / 1e12 / a.peak * 1e3:.0f} ms at {a.peak} TFLOP/s; "
           f"encode {a.frames * enc['conv'] / 1e15:.3f} PFLOP = {a.frames * enc['conv'] / 1e12 / a.peak * 1e3:.0f} ms")

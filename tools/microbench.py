@@ -258,9 +258,65 @@ def bench_upconv(args):
                               ref_absmax=float(ref.float().abs().max()))), flush=True)
 
 
+def bench_energy(args):
+    """Energy per call (NVML total-energy counter over a ~3 s loop) and time per call of the GroupNorm kernel families, of
+    bias+residual and of the two Upsample2D forms: the `fast` step runs under sw_power_cap, where a kernel that moves the same
+    bytes faster does not shorten the step unless it also spends less energy."""
+    import pynvml
+    import torch.nn.functional as F
+    from rollingdepth_b200 import _lib as L, ops
+    from rollingdepth_b200.sd2.layers import Upsample2D
+    dev = torch.device("cuda:0")
+    pynvml.nvmlInit()
+    h = pynvml.nvmlDeviceGetHandleByIndex(torch.cuda.current_device())
+    torch.backends.cudnn.benchmark = True
+
+    def measure(name, fn, seconds=3.0):
+        for _ in range(5):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.time()
+        for _ in range(20):
+            fn()
+        torch.cuda.synchronize()
+        iters = max(20, int(seconds / ((time.time() - t0) / 20)))
+        torch.cuda.synchronize()
+        time.sleep(0.5)
+        e0, t0 = pynvml.nvmlDeviceGetTotalEnergyConsumption(h), time.time()
+        for _ in range(iters):
+            fn()
+        torch.cuda.synchronize()
+        e1, t1 = pynvml.nvmlDeviceGetTotalEnergyConsumption(h), time.time()
+        clk = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+        print(json.dumps(dict(bench="energy", case=name, iters=iters, ms_per_call=(t1 - t0) / iters * 1e3,
+                              mJ_per_call=(e1 - e0) / iters, avg_watts=(e1 - e0) / 1e3 / (t1 - t0), sm_mhz_after=clk)), flush=True)
+
+    N, H, W, Cc = 12, 432, 768, 128
+    x = torch.randn(N, Cc, H, W, device=dev, dtype=torch.float16).contiguous(memory_format=torch.channels_last)
+    res = torch.randn_like(x)
+    w = torch.ones(Cc, device=dev, dtype=torch.float16)
+    b = torch.zeros(Cc, device=dev, dtype=torch.float16)
+    for mode, tag in ((0, "register-staged"), (2, "smem-staged")):
+        L.call("rd_groupnorm_set_staged", dev, mode)
+        measure(f"groupnorm+silu dec L3 12x432x768x128, {tag}", lambda: ops.group_norm_nhwc(x, 32, w, b, 1e-6, True))
+    L.call("rd_groupnorm_set_staged", dev, -1)
+    measure("bias+residual dec L3 12x432x768x128", lambda: ops.bias_residual_nhwc(x, bias=b, residual=res, inplace=False))
+    del x, res
+    m = Upsample2D(512).to(dev, torch.float16).to(memory_format=torch.channels_last).eval()
+    m.fused = True
+    m.conv.fused = True
+    xu = torch.randn(12, 512, 108, 192, device=dev, dtype=torch.float16).contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        for sp, tag in ((False, "nearest + 3x3"), (True, "sub-pixel 2x2 + interleave")):
+            m.subpixel = sp
+            measure(f"Upsample2D dec up1 12x108x192x512, {tag}", lambda: m(xu))
+        a = torch.randn(8192, 8192, device=dev, dtype=torch.float16)
+        measure("cuBLAS fp16 GEMM 8192^3 (context: a tensor-bound kernel)", lambda: a @ a)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["attn", "attn_fp32", "align", "gn", "upconv"])
+    ap.add_argument("what", choices=["attn", "attn_fp32", "align", "gn", "upconv", "energy"])
     ap.add_argument("--full", action="store_true")
     ap.add_argument("--small", action="store_true")
     ap.add_argument("--iters", type=int, default=200)
@@ -268,4 +324,4 @@ if __name__ == "__main__":
     ap.add_argument("--only", default="")
     ap.add_argument("--no-sdpa", action="store_true", help="skip the torch SDPA comparators")
     a = ap.parse_args()
-    {"attn": bench_attn, "attn_fp32": bench_attn_fp32, "align": bench_align, "gn": bench_gn, "upconv": bench_upconv}[a.what](a)
+    {"attn": bench_attn, "attn_fp32": bench_attn_fp32, "align": bench_align, "gn": bench_gn, "upconv": bench_upconv, "energy": bench_energy}[a.what](a)

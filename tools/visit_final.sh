@@ -1,6 +1,6 @@
 #!/bin/bash
-# Round-2 evidence visit (one B200): full -m gpu suite, smoke, bench (both arms, stage times, gpu_reference sample and full),
-# microbenchmarks incl. the config-5 sweep, ncu launch list of a 12-frame step, ncu --set full of the attention kernel.
+# End-of-round evidence visit (one B200): full -m gpu suite, smoke, bench (both arms, stage times), GroupNorm kernel-family A/B,
+# cfg1 preset, GroupNorm / Upsample2D microbenchmarks, ncu launch list of a 12-frame step.   usage: tools/visit_final.sh [TAG]
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
@@ -14,26 +14,20 @@ SMI=$!
 timeout 900 python bench.py --stage-times > gpurun_out/bench_$T.json 2> gpurun_out/bench_$T.err; tail -c 3500 gpurun_out/bench_$T.json; tail -2 gpurun_out/bench_$T.err
 kill $SMI
 timeout 600 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref_$T.json 2> gpurun_out/bench_ref_$T.err; tail -c 800 gpurun_out/bench_ref_$T.json
-timeout 600 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-output-check --gpu-reference full > gpurun_out/bench_gpuref_full_$T.json 2> gpurun_out/bench_gpuref_full_$T.err
+for ST in 0 1; do
+RD_GN_STAGED=$ST timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --gpu-reference off --stage-times --no-e2e > gpurun_out/bench_gn${ST}_$T.json 2> gpurun_out/bench_gn${ST}_$T.err
 python - <<PY
 import json
-d=json.loads(open('gpurun_out/bench_gpuref_full_$T.json').read().strip().splitlines()[-1])
-print('gpu_reference full:', d.get('gpu_reference'))
+d=json.loads(open('gpurun_out/bench_gn${ST}_$T.json').read().strip().splitlines()[-1])
+print('RD_GN_STAGED', $ST, round(d['value'],2), d['stage_ms_last_step_rank0'], d['output_check']['ok'], d['gpu_launches'])
 PY
-timeout 300 python bench.py --preset cfg1 --steps 3 --warmup 2 --no-cpu-baseline --gpu-reference off > gpurun_out/bench_cfg1_$T.json 2> gpurun_out/bench_cfg1_$T.err; tail -c 1200 gpurun_out/bench_cfg1_$T.json
-timeout 600 python tools/microbench.py attn > gpurun_out/mb_attn_$T.log 2>&1
-timeout 900 python tools/microbench.py attn --full > gpurun_out/mb_attn_sweep_$T.log 2>&1; tail -2 gpurun_out/mb_attn_sweep_$T.log | cut -c1-300
-timeout 300 python tools/microbench.py attn_fp32 > gpurun_out/mb_attn_fp32_$T.log 2>&1; cat gpurun_out/mb_attn_fp32_$T.log | cut -c1-300
-timeout 600 python tools/microbench.py align --iters 300 > gpurun_out/mb_align_$T.log 2>&1; cut -c1-260 gpurun_out/mb_align_$T.log
+done
+timeout 300 python bench.py --preset cfg1 --steps 3 --warmup 2 --no-cpu-baseline --gpu-reference off > gpurun_out/bench_cfg1_$T.json 2> gpurun_out/bench_cfg1_$T.err; tail -c 600 gpurun_out/bench_cfg1_$T.json
 timeout 300 python tools/microbench.py gn > gpurun_out/mb_gn_$T.log 2>&1; cut -c1-200 gpurun_out/mb_gn_$T.log
 if [ "${RD_SKIP_NCU:-0}" != "1" ]; then
 CMD="python bench.py --frames 12 --steps 1 --warmup 1 --no-cpu-baseline --no-output-check --gpu-reference off --coalign-its 200"
 timeout 300 $CMD > gpurun_out/plain_$T.log 2>&1 &&
 timeout 700 ncu --metrics gpu__time_duration.sum --clock-control none -c 14000 --csv --log-file gpurun_out/launches_$T.csv $CMD > gpurun_out/ncu_launches_$T.log 2>&1
 echo "launch list exit=$?"; wc -l gpurun_out/launches_$T.csv
-CMD2=(python tools/microbench.py attn --only "fast L0 B=16" --no-sdpa)
-timeout 300 "${CMD2[@]}" > gpurun_out/plain2_$T.log 2>&1 &&
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:xattn_fwd -s 3 -c 1 -f -o gpurun_out/prof_xattn_$T "${CMD2[@]}" > gpurun_out/ncu_xattn_$T.log 2>&1
-echo "ncu xattn exit=$?"
 fi
 ls gpurun_out | grep "_$T" | tr '\n' ' '
