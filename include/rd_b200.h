@@ -211,14 +211,6 @@ int rd_renorm(void* depth, int64_t n, const float* dev_minmax, rd_dtype dtype, v
  * pre_add: optional [N, C] vector (activation dtype) added to x first: y = act(GN(round(x + pre_add[n, c]))) --
  * the bias of the preceding (bias-free) convolution plus the projected time embedding (resnet.py:341-352). */
 int64_t rd_groupnorm_workspace_bytes(int N, int G);
-/* Kernels one rd_groupnorm_nhwc call launches for this shape: 3 (statistics, finalise, apply: the shared-memory-staged
- * kernels, used for samples of at least 16 MB whose pixel rows fit one CTA) or 2 (register-staged kernels); 0 = the shape
- * is not supported.  For launch accounting (bench.py `gpu_launches`). */
-int rd_groupnorm_launch_count(int HW, int C, int G, rd_dtype dtype);
-/* Kernel selection of rd_groupnorm_nhwc for tests and A/B measurements: 0 = register-staged kernels always, 1 = by sample
- * size (the default; environment RD_GN_STAGED overrides it at load time), 2 = shared-memory-staged kernels whenever the
- * shape is eligible, -1 = back to the default.  Process-wide, not thread-safe against concurrent calls. */
-int rd_groupnorm_set_staged(int mode);
 int rd_groupnorm_nhwc(const void* x, void* y, const void* gamma, const void* beta, const void* pre_add,
                       int N, int HW, int C, int G, float eps, int act, rd_dtype dtype,
                       void* workspace, int64_t workspace_bytes, void* stream);

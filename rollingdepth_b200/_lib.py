@@ -94,8 +94,6 @@ SIGNATURES = {
     "rd_merge": (_I, [_PP, _PRB, _P, _P, _P, _P, _P, _P, _P]),
     "rd_renorm": (_I, [_P, _I64, _P, _I, _P]),
     "rd_groupnorm_workspace_bytes": (_I64, [_I, _I]),
-    "rd_groupnorm_launch_count": (_I, [_I, _I, _I, _I]),
-    "rd_groupnorm_set_staged": (_I, [_I]),
     "rd_groupnorm_nhwc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _I, _I, _P, _I64, _P]),
     "rd_bias_residual_nhwc": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "rd_upsample_nearest_nhwc": (_I, [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P]),

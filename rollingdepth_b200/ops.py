@@ -120,7 +120,7 @@ def group_norm_nhwc(x: torch.Tensor, num_groups: int, weight: Optional[torch.Ten
     P = lambda t: L.ptr(t) if t is not None else None
     L.call("rd_groupnorm_nhwc", x.device, L.ptr(x), L.ptr(y), P(g), P(b), P(pre), N, HW, Cc, int(num_groups), float(eps),
            1 if silu else 0, L.dtype_code(x.dtype), L.ptr(ws), ws_bytes, L.stream_ptr(x.device))
-    L.count_launches(lib.rd_groupnorm_launch_count(HW, Cc, int(num_groups), L.dtype_code(x.dtype)))
+    L.count_launches(2)
     return y
 
 

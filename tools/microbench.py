@@ -259,12 +259,12 @@ def bench_upconv(args):
 
 
 def bench_energy(args):
-    """Energy per call (NVML total-energy counter over a ~3 s loop) and time per call of the GroupNorm kernel families, of
-    bias+residual and of the two Upsample2D forms: the `fast` step runs under sw_power_cap, where a kernel that moves the same
+    """Energy per call (NVML total-energy counter over a ~3 s loop) and time per call of GroupNorm, of bias+residual and of the
+    two Upsample2D forms: the `fast` step runs under sw_power_cap, where a kernel that moves the same
     bytes faster does not shorten the step unless it also spends less energy."""
     import pynvml
     import torch.nn.functional as F
-    from rollingdepth_b200 import _lib as L, ops
+    from rollingdepth_b200 import ops
     from rollingdepth_b200.sd2.layers import Upsample2D
     dev = torch.device("cuda:0")
     pynvml.nvmlInit()
@@ -296,10 +296,7 @@ def bench_energy(args):
     res = torch.randn_like(x)
     w = torch.ones(Cc, device=dev, dtype=torch.float16)
     b = torch.zeros(Cc, device=dev, dtype=torch.float16)
-    for mode, tag in ((0, "register-staged"), (2, "smem-staged")):
-        L.call("rd_groupnorm_set_staged", dev, mode)
-        measure(f"groupnorm+silu dec L3 12x432x768x128, {tag}", lambda: ops.group_norm_nhwc(x, 32, w, b, 1e-6, True))
-    L.call("rd_groupnorm_set_staged", dev, -1)
+    measure("groupnorm+silu dec L3 12x432x768x128", lambda: ops.group_norm_nhwc(x, 32, w, b, 1e-6, True))
     measure("bias+residual dec L3 12x432x768x128", lambda: ops.bias_residual_nhwc(x, bias=b, residual=res, inplace=False))
     del x, res
     m = Upsample2D(512).to(dev, torch.float16).to(memory_format=torch.channels_last).eval()
