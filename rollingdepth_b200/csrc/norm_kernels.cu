@@ -653,6 +653,26 @@ __global__ void __launch_bounds__(256) layernorm_rows_kernel(const T* __restrict
     }
 }
 
+// Split HW rows into chunks (one CTA each, `per_chunk_ctas` CTAs per chunk index over samples / slices) so that the launch is
+// whole waves of `slots` resident CTAs: minimises  waves x (rows per chunk + overhead_rows), chunks of at least min_rows rows.
+static void plan_wave_chunks(int HW, long long per_chunk_ctas, int min_rows, int overhead_rows, int slots, int max_chunks,
+                             int& chunks, int& rows) {
+    int cmax = HW / (min_rows > 0 ? min_rows : 1);
+    if (cmax < 1) cmax = 1;
+    if (cmax > max_chunks) cmax = max_chunks;
+    chunks = 1;
+    rows = HW;
+    double best = 1e300;
+    for (int c = 1; c <= cmax; ++c) {
+        const int rc = (HW + c - 1) / c;
+        const int cc = (HW + rc - 1) / rc;                       // chunks actually needed with rc rows each
+        const long long ctas = (long long)cc * per_chunk_ctas;
+        const double waves = (double)((ctas + slots - 1) / slots);
+        const double cost = waves * (double)(rc + overhead_rows);
+        if (cost < best * (1.0 - 1e-9)) { best = cost; chunks = cc; rows = rc; }
+    }
+}
+
 // channel slicing and CTA shape (needs C, G, cpg): Cs, CV, R; returns the slice count K or -1
 static int gn_plan_slices(GnParams& p, int es) {
     const int VN = 16 / es;
@@ -683,23 +703,9 @@ static int gn_plan(GnParams& p, int es) {
     // minimises  waves x (rows per chunk + a fixed per-CTA cost worth ~eight rows per thread: prologue that reduces the chunk
     // partials, first-load latency, reduction epilogue)  -- e.g. 12 samples -> 24 chunks = 288 CTAs = one full wave instead of 128
     // chunks = 5.2 waves of short CTAs (0.49 -> 0.69 of HBM on 12 x 108 x 192 x 512); 48 samples of 336 rows -> 6 chunks = 288 CTAs
-    // instead of 7 = 1.13 waves.  At least 4 vectors per thread per chunk.
-    constexpr int kGnU = 4;
-    const int slots = 2 * num_sms();
-    const int overhead_rows = 2 * kGnU * R;                        // (2, 8 and 24 rows per thread measured alike)
-    int max_chunks = p.HW / (kGnU * R);
-    if (max_chunks < 1) max_chunks = 1;
-    if (max_chunks > kGnMaxChunks) max_chunks = kGnMaxChunks;
-    int chunks = 1, rows = p.HW;
-    double best = 1e300;
-    for (int c = 1; c <= max_chunks; ++c) {
-        const int rc = (p.HW + c - 1) / c;
-        const int cc = (p.HW + rc - 1) / rc;                       // chunks actually needed with rc rows each
-        const long long ctas = (long long)cc * p.N * K;
-        const double waves = (double)((ctas + slots - 1) / slots);
-        const double cost = waves * (double)(rc + overhead_rows);
-        if (cost < best * (1.0 - 1e-9)) { best = cost; chunks = cc; rows = rc; }
-    }
+    // instead of 7 = 1.13 waves.  At least 4 vectors per thread per chunk; per-CTA cost worth 8 rows per thread (2, 8 and 24 measured alike).
+    int chunks, rows;
+    plan_wave_chunks(p.HW, (long long)p.N * K, 4 * R, 8 * R, 2 * num_sms(), kGnMaxChunks, chunks, rows);
     p.chunks = chunks;
     p.rows_per_chunk = rows;
     return 0;
@@ -785,7 +791,10 @@ int rd_bias_residual_nhwc(const void* x, const void* bias, const void* vec, cons
     while (p.CV % cvt) --cvt;
     int R = 256 / cvt; if (R < 1) R = 1; if (R > 32) R = 32;
     p.R = R;
-    int rows = 16 * R;                    // 16 rows per thread: four trips of four rows
+    // many short CTAs (16 rows per thread: four trips of four rows).  One wave of long CTAs, which is what GroupNorm wants
+    // (plan_wave_chunks), was measured SLOWER here: 0.87 / 0.85 / 0.78 of HBM against 0.98 / 0.92 / 0.83 on the decoder levels --
+    // this kernel has no per-CTA prologue or reduction to amortise, and short CTAs balance the DRAM channels dynamically.
+    int rows = 16 * R;
     int chunks = (HW + rows - 1) / rows;
     if (chunks > 4096) { chunks = 4096; rows = (HW + chunks - 1) / chunks; chunks = (HW + rows - 1) / rows; }
     p.chunks = chunks; p.rows_per_chunk = rows;
