@@ -1,6 +1,6 @@
 #!/bin/bash
-# End-of-round evidence visit (one B200): full -m gpu suite, smoke, bench (both arms, stage times), GroupNorm kernel-family A/B,
-# cfg1 preset, GroupNorm / Upsample2D microbenchmarks, ncu launch list of a 12-frame step.   usage: tools/visit_final.sh [TAG]
+# End-of-round evidence visit (one B200): full -m gpu suite, smoke, bench (both arms, stage times), cfg1 preset,
+# GroupNorm / bias+residual microbenchmark, ncu launch list of a 12-frame step.   usage: tools/visit_final.sh [TAG]
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
@@ -14,14 +14,6 @@ SMI=$!
 timeout 900 python bench.py --stage-times > gpurun_out/bench_$T.json 2> gpurun_out/bench_$T.err; tail -c 3500 gpurun_out/bench_$T.json; tail -2 gpurun_out/bench_$T.err
 kill $SMI
 timeout 600 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref_$T.json 2> gpurun_out/bench_ref_$T.err; tail -c 800 gpurun_out/bench_ref_$T.json
-for ST in 0 1; do
-RD_GN_STAGED=$ST timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --gpu-reference off --stage-times --no-e2e > gpurun_out/bench_gn${ST}_$T.json 2> gpurun_out/bench_gn${ST}_$T.err
-python - <<PY
-import json
-d=json.loads(open('gpurun_out/bench_gn${ST}_$T.json').read().strip().splitlines()[-1])
-print('RD_GN_STAGED', $ST, round(d['value'],2), d['stage_ms_last_step_rank0'], d['output_check']['ok'], d['gpu_launches'])
-PY
-done
 timeout 300 python bench.py --preset cfg1 --steps 3 --warmup 2 --no-cpu-baseline --gpu-reference off > gpurun_out/bench_cfg1_$T.json 2> gpurun_out/bench_cfg1_$T.err; tail -c 600 gpurun_out/bench_cfg1_$T.json
 timeout 300 python tools/microbench.py gn > gpurun_out/mb_gn_$T.log 2>&1; cut -c1-200 gpurun_out/mb_gn_$T.log
 if [ "${RD_SKIP_NCU:-0}" != "1" ]; then
