@@ -162,3 +162,53 @@ def test_subpixel_upsample_convolution_is_the_same_linear_map(H, W):
     assert pw.shape == (28, 5, 2, 2)
     got = phase_shuffle_reference(F.conv2d(x, pw, None, 1, 1), bias, H, W)
     assert float((got - ref).abs().max()) < 1e-12
+
+
+_ENCODE_WORKER = r"""
+import os, sys
+import torch, torch.distributed as dist
+sys.path.insert(0, os.environ["RD_ROOT"]); sys.path.insert(0, os.path.join(os.environ["RD_ROOT"], "tests"))
+import model_utils as mu
+from rollingdepth_b200.pipeline import RollingDepthPipeline
+from rollingdepth_b200.scheduler import DDIMSchedule
+from rollingdepth_b200.sd2.unet import UNet2DConditionModel
+from rollingdepth_b200.sd2.vae import AutoencoderKL
+dist.init_process_group("gloo")
+unet = mu.deterministic_init_(UNet2DConditionModel(**mu.TINY_UNET).eval(), seed=1)
+vae = mu.deterministic_init_(AutoencoderKL(**{k: v for k, v in mu.TINY_VAE.items() if not k.endswith("block_types")}).eval(), seed=2)
+pipe = RollingDepthPipeline(unet, vae, DDIMSchedule(**mu.DDIM_CFG), install_processor=False)
+with torch.no_grad():
+    for n_frames, H, W in ((1, 37, 51), (2, 40, 45), (5, 33, 32)):     # fewer frames than ranks; sizes that are not multiples of the stride
+        rgb = torch.rand(1, n_frames, 3, H, W, generator=torch.Generator().manual_seed(n_frames)) * 2 - 1
+        pipe.shard = type(pipe.shard)()                                 # one rank
+        ref = pipe.encode_rgb(rgb, 1)      # one frame per VAE call on every path: oneDNN's bits depend on the batch size
+        pipe.enable_sharding(output_ranks=None)
+        got = pipe.encode_rgb(rgb, 1, sharded=True)
+        assert got.shape == ref.shape and torch.equal(got, ref), (n_frames, H, W, got.shape, ref.shape)
+        lo, hi = pipe.shard.block(n_frames)                             # this rank uploads only its own block of frames
+        got2 = pipe.encode_rgb(rgb[:, lo:hi], 1, sharded=True, frame_block=(lo, hi), total_frames=n_frames)
+        assert torch.equal(got2, ref)
+        lat = ref[:, :, :4]
+        ref_d = pipe.decode_depth(lat, 1)
+        got_d = pipe.decode_depth(lat, 1, sharded=True)
+        assert torch.equal(got_d, ref_d)
+dist.destroy_process_group()
+print("rank ok")
+"""
+
+
+def test_sharded_vae_stages_world3_gloo_odd_sizes(tmp_path):
+    """frame-sharded VAE encode / decode with more ranks than frames and frame sizes that are not multiples of
+    the VAE stride -- every rank must size its gather slots identically (`_latent_hw`, `_decoded_hw`) and the gathered
+    result must equal the single-rank one bit for bit (gloo, CPU modules)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "worker.py"
+    script.write_text(_ENCODE_WORKER)
+    env = dict(os.environ, RD_ROOT=root, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=3",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
+                       capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.stdout.count("rank ok") == 3
