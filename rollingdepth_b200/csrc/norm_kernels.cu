@@ -745,8 +745,9 @@ int rd_groupnorm_nhwc(const void* x, void* y, const void* gamma, const void* bet
     cudaStream_t st = (cudaStream_t)stream;
     const int threads = p.CV * p.R;
     dim3 grid(p.chunks, N, C / p.Cs);
-    // (a cp.async staging ring holding eight 16-byte loads per thread in shared memory instead of four in registers was
-    //  measured 3-6 % SLOWER on the three decoder sizes -- tools/probes, profiles/r2_gn_variants.txt -- and is not kept)
+    // (measured and not kept -- tools/probes/gn_variants, profiles/r2_gn_variants.txt, profiles/r2_gn_staged.txt: a per-thread
+    //  cp.async staging ring, 3-6 % slower; a producer-warp + bulk-copy ring pair with a finalise kernel, no better than these two
+    //  kernels once the chunks are wave-sized; an apply pass of many short CTAs, -1...-10 %)
     const size_t sm_stats = 2 * (size_t)p.Cs * sizeof(double) + (2 * (size_t)p.R + 1) * p.Cs * sizeof(float);
     const size_t sm_apply = 2 * (size_t)p.Cs * sizeof(float);
     {   // up to 16 B * Cs + 8 B * R * Cs = 96 KB for the widest slice: opt in above the 48 KB default (per device)
