@@ -1,6 +1,6 @@
 """Generate tests/golden/* by running the REFERENCE's own code (build container only).
 
-    python oracle/gen_golden.py [--only snippets,coalign,xattn,ddim,pipeline,cfg1]
+    python oracle/gen_golden.py [--only snippets,coalign,xattn,ddim,pipeline,cfg1,cfg1_loss_floor]
 
 /root/reference is imported read-only with the recipe of SURVEY.md App. C (the
 `rollingdepth` package __init__ is bypassed, PyAV is stubbed, one transformers
@@ -233,6 +233,9 @@ def main():
     if "cfg1" in todo:        # not in the default list: minutes of CPU time (the full SD2 architecture)
         from oracle import gen_golden_cfg1
         gen_golden_cfg1.run(da, rp, GOLD)
+    if "cfg1_loss_floor" in todo:   # appends the reference's own loss-curve sensitivity floor to the cfg1 fixture
+        from oracle import gen_golden_cfg1
+        gen_golden_cfg1.loss_floor(da, rp, GOLD)
 
 
 if __name__ == "__main__":

@@ -122,7 +122,12 @@ def test_cfg1_fp32_matches_reference_run(golden_dir):
     assert worst < 2e-4
     assert res.depth_pred.shape == ref_depth.shape and torch.equal(res.depth_pred, res.depth_coaligned)
     assert ar <= 1e-3
-    assert head_rel <= 0.5 and loss_rel <= 1e-2
+    # loss level: the reference against itself with 1e-7 input noise moves the mean of the last 200 losses by 3e-3...1.7e-2
+    # (four seeds, fixture `floor_loss_tail_rel`, oracle/gen_golden_cfg1.py::loss_floor); tolerance = 3x the largest of them
+    loss_tol = 3.0 * float(np.max(g["floor_loss_tail_rel"]))
+    print(f"cfg1: loss-level tolerance {loss_tol:.2e} (reference's own floor per seed {np.array2string(g['floor_loss_tail_rel'], precision=2)})")
+    assert 1e-2 <= loss_tol <= 1e-1
+    assert head_rel <= 1e-3 and loss_rel <= loss_tol
     assert len(hist) == 2000
 
 
