@@ -32,6 +32,8 @@ def xattn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, scale: Optional
         raise L.RdError("head_dim axis must be contiguous")
     if out is None:
         out = torch.empty((B, Sq, H, D), dtype=q.dtype, device=q.device)
+    elif tuple(out.shape) != (B, Sq, H, D) or out.dtype != q.dtype or out.device != q.device or out.stride(3) != 1:
+        raise L.RdError(f"out must be a [B, Sq, H, D] = {(B, Sq, H, D)} tensor of q's dtype / device with a contiguous head_dim axis")
     scale = (1.0 / math.sqrt(D)) if scale is None else float(scale)
     L.call(
         "rd_xattn_fwd", q.device, L.ptr(q), L.ptr(k), L.ptr(v), L.ptr(out), B, H, Sq, Sk, D,
@@ -57,6 +59,8 @@ def ddim_step(model_output: torch.Tensor, sample: torch.Tensor, sqrt_alpha_t: fl
     mo, sm = model_output.contiguous(), sample.contiguous()
     if out is None:
         out = torch.empty_like(sm)
+    elif out.shape != sm.shape or out.dtype != sm.dtype or out.device != sm.device or not out.is_contiguous():
+        raise L.RdError("out must be a contiguous tensor of the sample's shape, dtype and device")
     L.call("rd_ddim_step", sm.device, L.ptr(mo), L.ptr(sm), L.ptr(out), sm.numel(), sqrt_alpha_t, sqrt_beta_t,
            sqrt_alpha_prev, sqrt_one_minus_alpha_prev, _PTYPE[prediction_type], float(clip),
            L.dtype_code(sm.dtype), L.stream_ptr(sm.device))
