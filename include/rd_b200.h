@@ -56,8 +56,8 @@ int rd_device_arch(void);
  * This is the strided view the reference's to_q/to_k/to_v Linear layers already produce
  * ([B, S, H*D] viewed as [B, S, H, D]) -- no head-major copy is needed.
  * D must be 64 (every SD2 UNet level).  RD_F16/RD_BF16 run on tcgen05 tensor cores with
- * fp32 accumulation; RD_F32 runs a plain fp32 FFMA kernel (one query row per thread, ex2.approx; |err| <= 1e-4 -- the
- * `paper` preset / cfg1 tolerance path, FMA-pipe bound: no tensor cores).
+ * fp32 accumulation; RD_F32 (the `paper` preset / cfg1 tolerance path, |err| <= 1e-4) runs the error-compensated 3xTF32
+ * tcgen05 kernel (hi/lo operand split, fp32 accumulation in TMEM); RD_XATTN_F32(1) selects the scalar fp32 FFMA kernel.
  * `flags`: 0 = default kernel; see RD_XATTN_* below (debug / A-B switches).
  */
 /* share of the softmax exponentials evaluated by a degree-3 polynomial on the FMA pipes instead of MUFU.EX2
