@@ -1,6 +1,6 @@
 """Generate tests/golden/* by running the REFERENCE's own code (build container only).
 
-    python oracle/gen_golden.py [--only snippets,coalign,xattn,ddim,pipeline,cfg1,cfg1_loss_floor]
+    python oracle/gen_golden.py [--only snippets,snippets_wide,coalign,xattn,ddim,pipeline,cfg1,cfg1_loss_floor]
 
 /root/reference is imported read-only with the recipe of SURVEY.md App. C (the
 `rollingdepth` package __init__ is bypassed, PyAV is stubbed, one transformers
@@ -70,6 +70,54 @@ def gen_snippets(da, rp):
     with open(os.path.join(GOLD, "snippets.json"), "w") as f:
         json.dump(cases, f)
     print("snippets:", len(cases), "cases")
+
+
+def snippet_digest(idx):
+    """Compact, exact fingerprint of a window index list (the wide fixture stores these instead of the lists)."""
+    import zlib
+    flat = [x for win in idx for x in win]
+    return dict(n=len(idx), first=idx[0], last=idx[-1], index_sum=sum(flat),
+                crc=zlib.crc32(",".join(map(str, flat)).encode()) & 0xFFFFFFFF)
+
+
+def gen_snippets_wide(da, rp):
+    """A wider sweep of the reference's scheduler than snippets.json (strides 1-4, sequences up to 1000 frames, snippet lengths
+    2-8, annealed dilations with several start / end pairs, every step) stored as digests, plus the reference's behaviour on
+    invalid requests (exception class).  tests/golden/snippets_wide.json."""
+    import logging
+    logging.disable(logging.WARNING)            # "Not every frame is covered" for strides > 1: expected
+    P = rp.RollingDepthPipeline
+    cases = []
+
+    def one(**a):
+        try:
+            idx = P.get_snippet_indice(a["i_step"], torch.zeros(a["total"]), a["seq_len"], a["snippet_len"], a["dilation_start"],
+                                       a["dilation_end"], a["stride"])
+            cases.append(dict(a, **snippet_digest(idx)))
+        except Exception as e:  # noqa: BLE001
+            cases.append(dict(a, error=type(e).__name__))
+
+    for seq_len in (3, 5, 9, 16, 31, 150, 1000):
+        for n in (2, 3, 5, 8):
+            for d in (1, 2, 7, 25, 60):
+                for stride in (1, 2, 3, 4):
+                    one(i_step=0, total=1, seq_len=seq_len, snippet_len=n, dilation_start=d, dilation_end=d, stride=stride)
+    for seq_len, n in ((150, 3), (1000, 3), (40, 4), (16, 2)):
+        for start, end in ((6, 1), (10, 3), (25, 1), (4, 4)):
+            for total in (3, 5, 10, 20):
+                for i_step in range(total):
+                    for stride in (1, 3):
+                        one(i_step=i_step, total=total, seq_len=seq_len, snippet_len=n, dilation_start=start,
+                            dilation_end=end, stride=stride)
+    one(i_step=0, total=1, seq_len=10, snippet_len=3, dilation_start=1, dilation_end=2, stride=1)     # gap_start < gap_end
+    one(i_step=0, total=1, seq_len=10, snippet_len=3, dilation_start=0, dilation_end=0, stride=1)     # negative gap
+    caps = [dict(seq_len=sl, snippet_len=n, dilation=d, capped=P.cap_max_dilation(seq_len=sl, snippet_len=n, dilation=d, verbose=False))
+            for sl in (2, 3, 7, 10, 16, 31, 150, 1000) for n in (1, 2, 3, 4, 8) for d in (1, 2, 6, 10, 25, 400)]
+    logging.disable(logging.NOTSET)
+    with open(os.path.join(GOLD, "snippets_wide.json"), "w") as f:
+        json.dump(dict(cases=cases, caps=caps), f, separators=(",", ":"))
+    n_err = sum("error" in c for c in cases)
+    print(f"snippets_wide: {len(cases)} scheduler cases ({n_err} of them invalid requests), {len(caps)} cap cases")
 
 
 # --------------------------------------------------------------------------- co-alignment
@@ -214,13 +262,15 @@ def gen_ddim(da, rp):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="snippets,coalign,xattn,ddim,pipeline")
+    ap.add_argument("--only", default="snippets,snippets_wide,coalign,xattn,ddim,pipeline")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     da, rp = import_reference()
     todo = args.only.split(",")
     if "snippets" in todo:
         gen_snippets(da, rp)
+    if "snippets_wide" in todo:
+        gen_snippets_wide(da, rp)
     if "coalign" in todo:
         gen_coalign(da, rp)
     if "xattn" in todo:
