@@ -1,6 +1,6 @@
 """Generate tests/golden/* by running the REFERENCE's own code (build container only).
 
-    python oracle/gen_golden.py [--only snippets,snippets_wide,coalign,xattn,ddim,pipeline,cfg1,cfg1_loss_floor]
+    python oracle/gen_golden.py [--only snippets,snippets_wide,coalign,xattn,ddim,ddim_wide,pipeline,cfg1,cfg1_loss_floor]
 
 /root/reference is imported read-only with the recipe of SURVEY.md App. C (the
 `rollingdepth` package __init__ is bypassed, PyAV is stubbed, one transformers
@@ -260,9 +260,60 @@ def gen_ddim(da, rp):
     print("ddim ok")
 
 
+DDIM_WIDE_CONFIGS = {
+    # tag: constructor kwargs on top of num_train_timesteps=1000 (the first one is RollingDepth's scheduler_config.json)
+    "rd": dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False, set_alpha_to_one=False,
+               steps_offset=1, prediction_type="v_prediction", timestep_spacing="trailing"),
+    "rd_one": dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False, set_alpha_to_one=True,
+                   steps_offset=0, prediction_type="v_prediction", timestep_spacing="trailing"),
+    "sd_eps": dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False, set_alpha_to_one=False,
+                   steps_offset=1, prediction_type="epsilon", timestep_spacing="leading"),
+    "lin_eps_clip": dict(beta_start=0.0001, beta_end=0.02, beta_schedule="linear", clip_sample=True, set_alpha_to_one=True,
+                         steps_offset=0, prediction_type="epsilon", timestep_spacing="leading"),
+    "lin_v_linspace": dict(beta_start=0.0001, beta_end=0.02, beta_schedule="linear", clip_sample=False, set_alpha_to_one=False,
+                           steps_offset=0, prediction_type="v_prediction", timestep_spacing="linspace"),
+    "sample_trail": dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False,
+                         set_alpha_to_one=False, steps_offset=1, prediction_type="sample", timestep_spacing="trailing"),
+    "sample_linspace_clip": dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=True,
+                                 clip_sample_range=0.8, set_alpha_to_one=True, steps_offset=0, prediction_type="sample",
+                                 timestep_spacing="linspace"),
+}
+DDIM_WIDE_STEPS = (1, 2, 3, 7, 20, 50, 1000)
+
+
+def gen_ddim_wide(da, rp):
+    """The reference's DDIMScheduler over a grid of configurations (beta schedule, spacing, prediction type, clipping,
+    set_alpha_to_one, steps_offset) x numbers of inference steps: timestep lists, and `step` outputs at the first / second /
+    middle / last timestep on small fp32 and fp16 inputs.  tests/golden/ddim_wide.npz; the CPU tier checks the oracle's
+    DDIMRef AND the product's host-side schedule (rollingdepth_b200/scheduler.py: timesteps + the four scalars it hands
+    to rd_ddim_step) against it."""
+    from diffusers import DDIMScheduler
+    out = {}
+    g = torch.Generator().manual_seed(23)
+    x32 = torch.randn(2, 4, 3, 3, generator=g)
+    v32 = torch.randn(2, 4, 3, 3, generator=g)
+    out["x"], out["v"] = x32.numpy(), v32.numpy()
+    n_steps = 0
+    for tag, kw in DDIM_WIDE_CONFIGS.items():
+        sch = DDIMScheduler(num_train_timesteps=1000, **kw)
+        for n in DDIM_WIDE_STEPS:
+            sch.set_timesteps(n)
+            ts = sch.timesteps.clone()
+            out[f"{tag}_ts{n}"] = ts.numpy()
+            for pos in sorted({0, min(1, len(ts) - 1), len(ts) // 2, len(ts) - 1}):
+                for dt, dn in ((torch.float32, "f32"), (torch.float16, "f16")):
+                    try:
+                        out[f"{tag}_n{n}_p{pos}_{dn}"] = sch.step(v32.to(dt), ts[pos], x32.to(dt)).prev_sample.numpy()
+                        n_steps += 1
+                    except IndexError:      # leading spacing + steps_offset with 1000 steps asks for timestep 1000
+                        out[f"{tag}_n{n}_p{pos}_{dn}_indexerror"] = np.array(int(ts[pos]))
+    np.savez_compressed(os.path.join(GOLD, "ddim_wide.npz"), **out)
+    print(f"ddim_wide: {len(DDIM_WIDE_CONFIGS)} configurations x {len(DDIM_WIDE_STEPS)} step counts, {n_steps} step outputs")
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="snippets,snippets_wide,coalign,xattn,ddim,pipeline")
+    ap.add_argument("--only", default="snippets,snippets_wide,coalign,xattn,ddim,ddim_wide,pipeline")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     da, rp = import_reference()
@@ -277,6 +328,8 @@ def main():
         gen_xattn(da, rp)
     if "ddim" in todo:
         gen_ddim(da, rp)
+    if "ddim_wide" in todo:
+        gen_ddim_wide(da, rp)
     if "pipeline" in todo:
         from oracle import gen_golden_pipeline
         gen_golden_pipeline.run(da, rp, GOLD)
