@@ -1,6 +1,6 @@
 """Generate tests/golden/* by running the REFERENCE's own code (build container only).
 
-    python oracle/gen_golden.py [--only snippets,snippets_wide,coalign,xattn,ddim,ddim_wide,pipeline,cfg1,cfg1_loss_floor]
+    python oracle/gen_golden.py [--only snippets,snippets_wide,aligner_geometry,coalign,xattn,ddim,ddim_wide,pipeline,cfg1,cfg1_loss_floor]
 
 /root/reference is imported read-only with the recipe of SURVEY.md App. C (the
 `rollingdepth` package __init__ is bypassed, PyAV is stubbed, one transformers
@@ -260,6 +260,47 @@ def gen_ddim(da, rp):
     print("ddim ok")
 
 
+def gen_aligner_geometry(da, rp):
+    """Index / shape bookkeeping of DepthAligner.run (depth_aligner.py:68-100) captured from the REFERENCE by intercepting its
+    call of `optimize`: sequence length, cropped + subsampled sizes, triplet index tables -- for a grid of frame counts, window
+    sizes, dilation sets, resolutions, borders and factors.  tests/golden/aligner_geometry.json; the CPU tier checks the
+    product's `DepthAligner._problem` (rd_coalign_problem_init, host C code) and `create_triplet_indices` against it."""
+    cases = []
+
+    class Stop(Exception):
+        pass
+
+    def grab(self, snippet_ls, indices_list, sequence_length):
+        raise Stop(dict(N=int(sequence_length), small=[list(t.shape) for t in snippet_ls],
+                        idx=[snippet_digest(ix.tolist()) for ix in indices_list]))
+
+    orig = da.DepthAligner.optimize
+    da.DepthAligner.optimize = grab
+    try:
+        grid = []
+        for (H, W) in ((44, 54), (47, 61), (30, 25), (256, 256)):
+            for (border, factor) in ((2, 10), (1, 4), (3, 7), (2, 1)):
+                for (N, w, dil) in ((7, 3, [1]), (12, 3, [1, 3]), (16, 3, [1, 4]), (16, 2, [1, 5, 8]), (21, 4, [1, 2, 5]),
+                                    (40, 3, [1, 10, 19]), (9, 8, [1])):
+                    grid.append((H, W, border, factor, N, w, dil))
+        for (H, W) in ((432, 768), (576, 1024)):
+            for (N, w, dil) in ((7, 3, [1, 2]), (9, 4, [1, 2])):
+                grid.append((H, W, 2, 10, N, w, dil))
+        for (H, W, border, factor, N, w, dil) in grid:
+            snips = [torch.zeros(N - (w - 1) * d, w, 1, H, W) for d in dil]
+            al = da.DepthAligner(device=torch.device("cpu"), factor=factor, border=border, num_iterations=1)
+            try:
+                al.run(snips, list(dil))
+                raise RuntimeError("optimize was not reached")
+            except Stop as st:
+                cases.append(dict(H=H, W=W, border=border, factor=factor, w=w, dilations=dil, n=[len(t) for t in snips], **st.args[0]))
+    finally:
+        da.DepthAligner.optimize = orig
+    with open(os.path.join(GOLD, "aligner_geometry.json"), "w") as f:
+        json.dump(cases, f, separators=(",", ":"))
+    print(f"aligner_geometry: {len(cases)} cases")
+
+
 DDIM_WIDE_CONFIGS = {
     # tag: constructor kwargs on top of num_train_timesteps=1000 (the first one is RollingDepth's scheduler_config.json)
     "rd": dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False, set_alpha_to_one=False,
@@ -313,7 +354,7 @@ def gen_ddim_wide(da, rp):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="snippets,snippets_wide,coalign,xattn,ddim,ddim_wide,pipeline")
+    ap.add_argument("--only", default="snippets,snippets_wide,aligner_geometry,coalign,xattn,ddim,ddim_wide,pipeline")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     da, rp = import_reference()
@@ -322,6 +363,8 @@ def main():
         gen_snippets(da, rp)
     if "snippets_wide" in todo:
         gen_snippets_wide(da, rp)
+    if "aligner_geometry" in todo:
+        gen_aligner_geometry(da, rp)
     if "coalign" in todo:
         gen_coalign(da, rp)
     if "xattn" in todo:

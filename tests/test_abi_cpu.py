@@ -96,6 +96,35 @@ def test_balanced_chunks():
             assert max(sizes) <= m and max(sizes) - min(sizes) <= 1 and len(ch) == -(-n // m)
 
 
+def test_aligner_geometry_matches_reference(golden_dir):
+    """Index / shape bookkeeping of `DepthAligner.run` (depth_aligner.py:68-100): the product's `_problem`
+    (rd_coalign_problem_init: host C code of the library, no device) and `create_triplet_indices` against what the REFERENCE
+    hands to its `optimize` -- sequence length, cropped + subsampled sizes, snippet counts, triplet index tables -- for 116
+    combinations of frame count, window, dilations, resolution, border and factor (tests/golden/aligner_geometry.json)."""
+    import json
+    import zlib
+    import torch
+    from rollingdepth_b200.depth_aligner import DepthAligner
+    cases = json.load(open(os.path.join(golden_dir, "aligner_geometry.json")))
+    assert len(cases) >= 116
+    for c in cases:
+        al = DepthAligner(device=torch.device("cuda", 0), factor=c["factor"], border=c["border"])
+        snips = [torch.empty((n, c["w"], 1, c["H"], c["W"]), device="meta") for n in c["n"]]
+        pb = al._problem(snips, c["dilations"])
+        assert pb.N == c["N"] and pb.G == len(c["dilations"]) and pb.w == c["w"], c
+        row0 = 0
+        for g, small in enumerate(c["small"]):
+            assert [pb.n[g], pb.w, 1, pb.Hs, pb.Ws] == small, (c, g)
+            assert pb.row0[g] == row0
+            row0 += pb.n[g]
+            idx = al.create_triplet_indices(pb.N, pb.d[g] - 1, pb.w).tolist()
+            flat = [x for win in idx for x in win]
+            got = dict(n=len(idx), first=idx[0], last=idx[-1], index_sum=sum(flat),
+                       crc=zlib.crc32(",".join(map(str, flat)).encode()) & 0xFFFFFFFF)
+            assert got == c["idx"][g], (c, g)
+        assert pb.n_total == row0 and pb.P == pb.Hs * pb.Ws and pb.P_pad % 8 == 0 and 0 <= pb.P_pad - pb.P < 8
+
+
 def test_product_snippet_scheduler_matches_reference(golden_dir):
     """The PRODUCT copy of get_snippet_indice / cap_max_dilation (rollingdepth_pipeline.py:465-515) against all
     reference-generated cases (integer work: exact)."""
