@@ -1,6 +1,6 @@
 """Generate tests/golden/* by running the REFERENCE's own code (build container only).
 
-    python oracle/gen_golden.py [--only snippets,snippets_wide,aligner_geometry,coalign,xattn,ddim,ddim_wide,pipeline,cfg1,cfg1_loss_floor]
+    python oracle/gen_golden.py [--only snippets,snippets_wide,forward_args,aligner_geometry,coalign,xattn,ddim,ddim_wide,pipeline,cfg1,cfg1_loss_floor]
 
 /root/reference is imported read-only with the recipe of SURVEY.md App. C (the
 `rollingdepth` package __init__ is bypassed, PyAV is stubbed, one transformers
@@ -301,6 +301,64 @@ def gen_aligner_geometry(da, rp):
     print(f"aligner_geometry: {len(cases)} cases")
 
 
+FORWARD_ARG_CASES = [
+    # (seq_len, forward kwargs that differ from the defaults below)
+    (16, dict(dilations=[2, 4])),
+    (16, dict(dilations=[1, 4], snippet_lengths=[3, 3])),
+    (16, dict(dilations=[1, 4, 6], snippet_lengths=[3, 4])),
+    (16, dict(dilations=[1, 4, 6], init_infer_steps=[1, 2])),
+    (16, dict(dilations=[1, 4], init_infer_steps=[0])),
+    (16, dict(dilations=[1, 4], init_infer_steps=[1, 0])),
+    (16, dict(dilations=[1, 4, 6], strides=[1, 2])),
+    (16, dict(dilations=[1, 4], strides=[2])),
+    (16, dict(dilations=[1, 4, 6], strides=[1, 2, 1])),
+    (16, dict(dilations=[1, 10, 25])),
+    (16, dict(dilations=[1, 10, 25], cap_dilation=False)),
+    (150, dict(dilations=[1, 10, 25], refine_start_dilation=6)),
+    (150, dict(dilations=[1, 25, 80], snippet_lengths=[3, 4, 2])),
+    (10, dict(dilations=[1, 25], refine_start_dilation=6, refine_snippet_len=4)),
+    (7, dict(dilations=[25, 1], snippet_lengths=[2, 3], init_infer_steps=[2, 1])),
+]
+FORWARD_ARG_DEFAULTS = dict(cap_dilation=True, snippet_lengths=[3], init_infer_steps=[1], strides=[1], coalign_kwargs=None,
+                            refine_step=0, refine_snippet_len=3, refine_start_dilation=6, generator=None, verbose=False,
+                            max_vae_bs=4, unload_snippet=False)
+
+
+def gen_forward_args(da, rp):
+    """Argument handling of RollingDepthPipeline.forward (rollingdepth_pipeline.py:213-258) recorded from the REFERENCE: the
+    exception class and message of every rejected call, and for accepted calls the caller's `dilations` list after the in-place
+    capping (the first stage after the checks, encode_rgb, is intercepted).  tests/golden/forward_args.json."""
+    import copy
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import model_utils as mu
+    from diffusers import AutoencoderKL, DDIMScheduler, UNet2DConditionModel
+    unet = UNet2DConditionModel(**mu.TINY_UNET).eval()
+    vae = AutoencoderKL(**mu.TINY_VAE).eval()
+    pipe = rp.RollingDepthPipeline(unet=unet, vae=vae, scheduler=DDIMScheduler(**mu.DDIM_CFG), text_encoder=None, tokenizer=None)
+
+    class Reached(Exception):
+        pass
+
+    def stop(*a, **k):
+        raise Reached()
+    pipe.encode_rgb = stop
+    out = []
+    for seq_len, kw in FORWARD_ARG_CASES:
+        args = copy.deepcopy(dict(FORWARD_ARG_DEFAULTS, **kw))
+        rec = dict(seq_len=seq_len, kwargs=copy.deepcopy(kw))
+        try:
+            pipe.forward(input_frames=torch.zeros(1, seq_len, 3, 16, 16), **args)
+            raise RuntimeError("encode_rgb was not reached")
+        except Reached:
+            rec.update(accepted=True, dilations_after=list(args["dilations"]))
+        except (AssertionError, NotImplementedError) as e:
+            rec.update(accepted=False, error=type(e).__name__, message=str(e))
+        out.append(rec)
+    with open(os.path.join(GOLD, "forward_args.json"), "w") as f:
+        json.dump(out, f, indent=0)
+    print(f"forward_args: {len(out)} calls, {sum(not r['accepted'] for r in out)} rejected")
+
+
 DDIM_WIDE_CONFIGS = {
     # tag: constructor kwargs on top of num_train_timesteps=1000 (the first one is RollingDepth's scheduler_config.json)
     "rd": dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False, set_alpha_to_one=False,
@@ -354,7 +412,7 @@ def gen_ddim_wide(da, rp):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="snippets,snippets_wide,aligner_geometry,coalign,xattn,ddim,ddim_wide,pipeline")
+    ap.add_argument("--only", default="snippets,snippets_wide,forward_args,aligner_geometry,coalign,xattn,ddim,ddim_wide,pipeline")
     args = ap.parse_args()
     os.makedirs(GOLD, exist_ok=True)
     da, rp = import_reference()
@@ -363,6 +421,8 @@ def main():
         gen_snippets(da, rp)
     if "snippets_wide" in todo:
         gen_snippets_wide(da, rp)
+    if "forward_args" in todo:
+        gen_forward_args(da, rp)
     if "aligner_geometry" in todo:
         gen_aligner_geometry(da, rp)
     if "coalign" in todo:

@@ -247,3 +247,32 @@ def test_oracle_chain_at_full_sd2_architecture_matches_reference_cfg1(golden_dir
                 ref = torch.from_numpy(g[f"snip{gi}_{r}"])
                 worst = max(worst, float((dec[:, :, ::2, ::2] - ref).abs().max()) / max(1.0, float(ref.abs().max())))
     assert worst < 5e-5, worst      # fp32 on both sides; measured 9e-6 of the range (max-abs 1.1e-5: conv / GEMM blocking only)
+
+
+def test_forward_argument_handling_matches_reference(golden_dir):
+    """`RollingDepthPipeline.forward` argument checks and in-place dilation capping (rollingdepth_pipeline.py:213-258)
+    against what the REFERENCE's forward does with the same calls (tests/golden/forward_args.json, recorded by
+    oracle/gen_golden.py::gen_forward_args): rejected calls raise the same exception class with the same message; accepted
+    calls leave the caller's `dilations` list capped in place exactly like the reference (Q6) -- and then, on this CPU-resident
+    pipeline, stop with RdError because there is no CPU fallback."""
+    import copy
+    from oracle.gen_golden import FORWARD_ARG_DEFAULTS
+    from rollingdepth_b200._lib import RdError
+    from rollingdepth_b200.pipeline import RollingDepthPipeline
+    from rollingdepth_b200.scheduler import DDIMSchedule
+    unet, vae = _tiny()
+    pipe = RollingDepthPipeline(unet, vae, DDIMSchedule(**mu.DDIM_CFG), install_processor=False)
+    cases = json.load(open(os.path.join(golden_dir, "forward_args.json")))
+    assert len(cases) >= 15 and sum(not c["accepted"] for c in cases) >= 9
+    for c in cases:
+        args = copy.deepcopy(dict(FORWARD_ARG_DEFAULTS, **c["kwargs"]))
+        frames = torch.zeros(1, c["seq_len"], 3, 16, 16)
+        if c["accepted"]:
+            with pytest.raises(RdError, match="no CPU fallback"):
+                pipe.forward(input_frames=frames, **args)
+            assert list(args["dilations"]) == c["dilations_after"], c
+        else:
+            exc = {"AssertionError": AssertionError, "NotImplementedError": NotImplementedError}[c["error"]]
+            with pytest.raises(exc) as ei:
+                pipe.forward(input_frames=frames, **args)
+            assert str(ei.value) == c["message"], c
