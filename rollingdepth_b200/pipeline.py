@@ -567,20 +567,28 @@ class RollingDepthPipeline:
                 pred = self.single_step(rgb_in, depth_in, t_current, text)
                 self.scheduler.step(pred, t_current, depth_in, out=mine[b0:b1])
             preds = self.shard.gather_(buf, n_win)
-            # accumulate per frame in the reference's order (windows by ascending start => j = n-1 ... 0), with the
-            # reference's in-dtype rounding after every += (:621-624), then average by the integer count (:629)
-            new = torch.zeros_like(depth_latent_old[0])
-            count = torch.zeros(seq_len, device=self.device, dtype=torch.int32)
-            for j in range(snippet_len - 1, -1, -1):
-                new[j * g: j * g + n_win] += preds[:, j]
-                count[j * g: j * g + n_win] += 1
-            # `assert torch.all(count_depth_latent_new > 0)` (:628) is pure index logic: frame f is covered iff
-            # f - j*g lies in [0, n_win) for some j, i.e. the w blocks [j*g, j*g + n_win) leave no gap -- checked on
-            # the host instead of synchronising on `count`
-            assert snippet_len == 1 and n_win == seq_len or snippet_len > 1 and n_win >= g, \
-                "refinement windows do not cover every frame"
-            depth_latent_new = (new / count[:, None, None, None])[None]
+            depth_latent_new = self._average_windows(preds, g, seq_len)[None]
         return depth_latent_new
+
+    @staticmethod
+    def _average_windows(preds: torch.Tensor, g: int, seq_len: int) -> torch.Tensor:
+        """Per-frame average of the rolling windows' predictions (:585-629).  `preds` [n_win, n, C, h, w]: window k covers
+        frames k + j*g (stride 1, so window starts are 0 .. n_win-1).  Accumulates per frame in the reference's order
+        (windows by ascending start => j = n-1 ... 0) with the reference's in-dtype rounding after every += (:621-624),
+        then divides by the integer count (:629): bit-identical to the reference's loop over windows."""
+        n_win, snippet_len = preds.shape[:2]
+        # `assert torch.all(count_depth_latent_new > 0)` (:628) is pure index logic: frame f is covered iff
+        # f - j*g lies in [0, n_win) for some j, i.e. the w blocks [j*g, j*g + n_win) leave no gap -- checked on
+        # the host instead of synchronising on `count`
+        assert (snippet_len - 1) * g + n_win == seq_len, (snippet_len, g, n_win, seq_len)
+        assert snippet_len == 1 and n_win == seq_len or snippet_len > 1 and n_win >= g, \
+            "refinement windows do not cover every frame"
+        new = torch.zeros((seq_len, *preds.shape[2:]), dtype=preds.dtype, device=preds.device)
+        count = torch.zeros(seq_len, device=preds.device, dtype=torch.int32)
+        for j in range(snippet_len - 1, -1, -1):
+            new[j * g: j * g + n_win] += preds[:, j]
+            count[j * g: j * g + n_win] += 1
+        return new / count[:, None, None, None]
 
     # ------------------------------------------------------------------ UNet step (:635-663)
     def single_step(self, rgb_latent: torch.Tensor, depth_latent: torch.Tensor, timestep: int,

@@ -276,3 +276,33 @@ def test_forward_argument_handling_matches_reference(golden_dir):
             with pytest.raises(exc) as ei:
                 pipe.forward(input_frames=frames, **args)
             assert str(ei.value) == c["message"], c
+
+
+@pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16, torch.float32])
+def test_refine_window_average_is_bit_identical_to_the_reference_loop(dtype):
+    """`RollingDepthPipeline._average_windows` (vectorised over the windows of one refinement step) against the reference's
+    formulation (rollingdepth_pipeline.py:585-629: `new *= 0`, then for every window in ascending order `new[:, idx] += pred`
+    and `count[:, idx] += 1`, then `new / count` with an int32 count): identical bits in fp16 / bf16 / fp32, because the
+    per-frame order of the in-dtype additions is the same (ascending window start = descending position in the window)."""
+    from rollingdepth_b200.pipeline import RollingDepthPipeline as P
+    g0 = torch.Generator().manual_seed(7)
+    for seq_len, n, start, total in ((16, 3, 5, 10), (40, 3, 6, 5), (30, 4, 4, 7), (12, 2, 6, 4), (9, 1, 1, 2)):
+        for i_step in range(total):
+            idx_ls = P.get_snippet_indice(i_step, [0] * total, seq_len, n, start if n > 1 else 1, 1, 1)
+            n_win = len(idx_ls)
+            gap = idx_ls[0][1] - idx_ls[0][0] if n > 1 else 1
+            preds = (torch.randn(n_win, n, 4, 3, 5, generator=g0) * 3).to(dtype)
+            old = torch.randn(1, seq_len, 4, 3, 5, generator=g0).to(dtype)
+            new = old.clone()
+            new *= 0.0
+            count = torch.zeros((1, seq_len, 1, 1, 1)).int()
+            for k, idx in enumerate(idx_ls):
+                new[:, idx, :, :, :] += preds[k][None].clone()
+                count[:, idx, 0, 0, 0] += 1
+            if not bool(torch.all(count > 0)):
+                with pytest.raises(AssertionError):
+                    P._average_windows(preds, gap, seq_len)
+                continue
+            ref = new / count
+            got = P._average_windows(preds, gap, seq_len)[None]
+            assert got.dtype == ref.dtype == dtype and torch.equal(got, ref), (seq_len, n, start, i_step)
