@@ -306,3 +306,38 @@ def test_refine_window_average_is_bit_identical_to_the_reference_loop(dtype):
             ref = new / count
             got = P._average_windows(preds, gap, seq_len)[None]
             assert got.dtype == ref.dtype == dtype and torch.equal(got, ref), (seq_len, n, start, i_step)
+
+
+def test_product_vae_wrappers_and_single_step_match_the_oracle_on_cpu():
+    """`RollingDepthPipeline.encode_rgb / decode_depth / single_step` are plain host code around the modules (no kernel of the
+    library): on CPU they must agree with the oracle's restatement of rollingdepth_pipeline.py:635-740 -- posterior mean (not a
+    sample), the 0.18215 factors, the mean over the decoder's three channels, frame order across chunks -- for chunk sizes that
+    divide the frame count and for ones that do not (the product balances its chunks, the reference takes fixed ones: same
+    frames, other batch compositions, so equality is to fp32 conv round-off, not bit for bit)."""
+    from rollingdepth_b200.pipeline import RollingDepthPipeline
+    from rollingdepth_b200.scheduler import DDIMSchedule
+    unet, vae = _tiny()
+    pipe = RollingDepthPipeline(unet, vae, DDIMSchedule(**mu.DDIM_CFG), install_processor=False)
+    g = torch.Generator().manual_seed(3)
+    frames = torch.rand(1, 7, 3, 24, 40, generator=g) * 2 - 1
+    with torch.no_grad():
+        ref_lat = opipe.encode_rgb(vae, frames, 4)
+        for bs in (1, 3, 4, 7, 36):
+            lat = pipe.encode_rgb(frames, max_batch_size=bs)
+            assert lat.shape == ref_lat.shape == (1, 7, 4, 12, 20)
+            assert float((lat - ref_lat).abs().max()) < 1e-5, bs
+        snip = ref_lat[:, :6].reshape(2, 3, 4, 12, 20)                        # two "snippets" of three frames
+        ref_dec = opipe.decode_depth(vae, snip, 4)
+        for bs in (1, 4, 5, 36):
+            dec = pipe.decode_depth(snip, max_batch_size=bs)
+            assert dec.shape == ref_dec.shape == (2, 3, 1, 24, 40)
+            assert float((dec - ref_dec).abs().max()) < 1e-5, bs
+        out = torch.empty(2, 3, 1, 24, 40)
+        assert pipe.decode_depth(snip, max_batch_size=4, out=out) is out and float((out - ref_dec).abs().max()) < 1e-5
+        # one UNet call over b snippets at once == the reference's one call per snippet (num_view rearrange is per batch element)
+        text = torch.randn(1, 2, 32, generator=g)
+        rgb, dep = snip, torch.randn(2, 3, 4, 12, 20, generator=g)
+        both = pipe.single_step(rgb, dep, 999, text)
+        for b in range(2):
+            one = opipe.single_step(unet, rgb[b:b + 1], dep[b:b + 1], 999, text)
+            assert float((both[b:b + 1] - one).abs().max()) < 2e-5
